@@ -1,0 +1,173 @@
+/*
+ * b200nufft.h -- C ABI of libb200nufft.so: the B200 (sm_100a) replacement for PyNUFFT's
+ * device NUFFT hot path.
+ *
+ * The reference has no FFI: its device path is a set of reikna/PyCUDA kernel launches made
+ * from Python (nufft/_nufft_class_methods_device.py).  Each entry point below names the
+ * reference interface it replaces (paths relative to the pynufft checkout); INTEGRATION.md
+ * shows the ctypes binding a pynufft maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; b200nufft_last_error() gives the text
+ *   - all device pointers are plain CUDA device pointers on the plan's device; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous and
+ *     never synchronise unless documented
+ *   - complex64 = interleaved float pairs (b200_c64)
+ *   - "image" arrays have the reference layout Nd+(B,), batch innermost: element (n, c) at
+ *     n*B + c (linalg/nufft_hsa.py:225-227); B = nb of the call
+ *   - "data" arrays y have the reference layout (M, B): element (m, c) at m*B + c
+ *   - "grid" arrays are COIL-MAJOR: nb contiguous Kd grids, element (idx, c) at c*prod(Kd)+idx.
+ *     The Python layer exposes them as Kd+(B,) views of that storage.
+ *   - one plan is not re-entrant across streams (it owns scratch grids).
+ */
+#ifndef B200NUFFT_H
+#define B200NUFFT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float re, im; } b200_c64;
+typedef struct b200nufft_plan_s* b200nufft_plan_t;
+
+#define B200NUFFT_MAX_DIM 3
+#define B200NUFFT_MAX_J 16
+#define B200NUFFT_MAX_L 32
+
+/* ---- status ------------------------------------------------------------------------------ */
+const char* b200nufft_last_error(void);
+int b200nufft_version(void);
+
+/* ---- plan: replaces helper.plan(format='pELL') + _plan_device/_offload_device -------------
+ * (src/_helper/helper.py:620-802, nufft/_nufft_class_methods_device.py:98-254,
+ *  batch from linalg/nufft_hsa.py:152-242)
+ *   om        : (M, ndim) float64, row-major, host or device pointer, radians in [-pi, pi]
+ *   alpha     : ndim * B200NUFFT_MAX_L doubles; alpha[d*MAX_L + l], l = 0..alpha_len[d]-1
+ *               (float32 values of helper.nufft_alpha_kb_fit :910-958 widened to double)
+ *   Tmat      : ndim * MAX_J*MAX_J doubles; T_d[j1*Jd[d] + j2] at Tmat[d*MAX_J*MAX_J + ...]
+ *               (helper.nufft_T :1060-1083)
+ *   sn        : sum(Nd) floats, the concatenated 1-D scaling vectors (helper.Tensor_sn :246-282)
+ * The per-sample part (helper.nufft_offset :900-907, OMEGA_k :164-210, nufft_r :1086-1117,
+ * min_max :606-618, OMEGA_u :148-162) runs on the GPU in float64; samples are then bin-sorted
+ * by the tile that holds their first neighbour (stable).  Synchronises `stream` before return. */
+int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim,
+                          const int32_t* Nd, const int32_t* Kd, const int32_t* Jd,
+                          int64_t M, const double* om, int batch,
+                          const double* alpha, const int32_t* alpha_len,
+                          const double* Tmat, const float* sn, void* stream);
+/* replaces NUFFT.release (nufft/_nufft_class_methods_device.py:653-683) */
+int b200nufft_plan_destroy(b200nufft_plan_t plan);
+
+/* ---- plan introspection for parity tests (original sample order) ---------------------------
+ * kindx : (M, sum(Jd)) uint32, udata : (M, sum(Jd)) complex64 -- exactly st['pELL'].kindx/.udata
+ *         (helper.create_partialELL :346-393); k0 : (M, ndim) int32 = floor(om/gam - J/2);
+ * perm  : (M,) int32, perm[i] = original index of the i-th sample in bin-sorted order;
+ * tile  : 2*ndim int32 (HOST): tile edges then sub-tile edges; the bin key of a sample is
+ *         key = tile_linear * subtiles_per_tile + subtile_linear of its first neighbour
+ *         (k0+1) mod K, both C-order; perm == stable argsort(key).  Other outputs are DEVICE.   */
+int b200nufft_plan_get_kindx(b200nufft_plan_t plan, uint32_t* kindx, void* stream);
+int b200nufft_plan_get_udata(b200nufft_plan_t plan, b200_c64* udata, void* stream);
+int b200nufft_plan_get_k0(b200nufft_plan_t plan, int32_t* k0, void* stream);
+int b200nufft_plan_get_perm(b200nufft_plan_t plan, int32_t* perm, void* stream);
+int b200nufft_plan_get_tile(b200nufft_plan_t plan, int32_t* tile_host);
+int64_t b200nufft_plan_bytes(b200nufft_plan_t plan);
+
+/* ---- stages ----------------------------------------------------------------------------------
+ * x2xx : out = in * sn (div=0) or in / sn (div=1), image layout.  Replaces cTensorMultiply
+ *        (src/re_subroutine.py:145-201) as used by _x2xx_device/_xx2x_device
+ *        (nufft/_nufft_class_methods_device.py:314-331, 451-468) and the CG un-scale
+ *        (linalg/solve_device.py:472-480).  in == out allowed.                               */
+int b200nufft_x2xx(b200nufft_plan_t plan, const b200_c64* in, b200_c64* out, int nb, int div,
+                   void* stream);
+/* scale_pad : grid = zero-pad( x * [sn if apply_sn] * [sens if sens] ) into the [0,Nd) corner,
+ *        writing EVERY grid element (no separate fill).  x is image layout with nb coils, or a
+ *        single-coil image broadcast to nb coils when x_single != 0 (cPopulate).  sens is image
+ *        layout (nb coils) or NULL.  Replaces cTensorMultiply + fill + cTensorCopy(+1)
+ *        (re_subroutine.py:98-201; _x2xx_device, _xx2k_device :314-359) and s2x
+ *        (cPopulate + cMultiplyVecInplace, linalg/nufft_hsa.py:358-388).                     */
+int b200nufft_scale_pad(b200nufft_plan_t plan, const b200_c64* x, b200_c64* grid, int nb,
+                        int apply_sn, int x_single, const b200_c64* sens, void* stream);
+/* fft : in-place c2c FFT of nb coil-major grids over all axes; inverse = 0 forward, 1 inverse
+ *        normalised by 1/prod(Kd) (numpy.fft.ifftn convention), 2 inverse unnormalised.  Replaces reikna.fft.FFT
+ *        (_nufft_class_methods_device.py:246-249, 358, 431).  cuFFT.                          */
+int b200nufft_fft(b200nufft_plan_t plan, b200_c64* grid, int nb, int inverse, void* stream);
+/* interp : y[m,c] = sum_j w[m,j] grid_c[col(m,j)].  Replaces pELL_spmv_mCoil
+ *        (re_subroutine.py:751-835; _k2y_device :361-386).                                    */
+int b200nufft_interp(b200nufft_plan_t plan, const b200_c64* grid, b200_c64* y, int nb,
+                     void* stream);
+/* grid : grid_c[col(m,j)] = sum_m conj(w[m,j]) y[m,c]; zero-fills the grid itself.  Replaces
+ *        pELL_spmvh_mCoil + atomic_add_float2 (re_subroutine.py:527-596, 275-287;
+ *        _y2k_device :388-422).                                                               */
+int b200nufft_gridding(b200nufft_plan_t plan, const b200_c64* y, b200_c64* grid, int nb,
+                       void* stream);
+/* crop_scale : image = crop(grid corner) * f, f = 1 (mode 0), sn (mode 1), 1/sn (mode 2).
+ *        With combine != 0 the nb coils are reduced to ONE image:
+ *        out[n] = (1/nb) sum_c conj(sens[n,c]) * crop_c[n] * f   (sens NULL = ones).
+ *        Replaces cTensorCopy(-1) + cTensorMultiply (_k2xx_device/_xx2x_device :425-468) and x2s
+ *        (cMultiplyConjVecInplace + cAggregate, linalg/nufft_hsa.py:628-656).                 */
+int b200nufft_crop_scale(b200nufft_plan_t plan, const b200_c64* grid, b200_c64* x, int nb,
+                         int mode, int combine, const b200_c64* sens, void* stream);
+
+/* ---- compositions (plan-owned scratch grids) -------------------------------------------------
+ * forward  : _forward_device  (:555-572)  x image(nb) -> y (M, nb)
+ * adjoint  : _adjoint_device  (:617-633)  y (M, nb)   -> x image(nb)        (= A^H y / prod(Kd))
+ * one2many / many2one: forward_one2many / adjoint_many2one (linalg/nufft_hsa.py:723-769)        */
+int b200nufft_forward(b200nufft_plan_t plan, const b200_c64* x, b200_c64* y, int nb, void* stream);
+int b200nufft_adjoint(b200nufft_plan_t plan, const b200_c64* y, b200_c64* x, int nb, void* stream);
+int b200nufft_forward_one2many(b200nufft_plan_t plan, const b200_c64* s, const b200_c64* sens,
+                               b200_c64* y, int nb, void* stream);
+int b200nufft_adjoint_many2one(b200nufft_plan_t plan, const b200_c64* y, const b200_c64* sens,
+                               b200_c64* s, int nb, void* stream);
+/* Host-buffer variants: the reference's NUFFT.forward / NUFFT.adjoint host wrappers
+ * (_forward_host/_adjoint_host, nufft/_nufft_class_methods_cpu.py:366-379): H2D copy, device
+ * path, D2H copy, stream synchronise.  x_host/y_host are host pointers (pinned or pageable).   */
+int b200nufft_forward_host(b200nufft_plan_t plan, const b200_c64* x_host, b200_c64* y_host,
+                           int nb, void* stream);
+int b200nufft_adjoint_host(b200nufft_plan_t plan, const b200_c64* y_host, b200_c64* x_host,
+                           int nb, void* stream);
+
+/* ---- solver vector ops (fused replacements of the element-wise kernels the device solvers
+ *      launch one by one, linalg/solve_device.py:351-481 and :74-275) --------------------------
+ * Scalars stay on the device as double pairs (re, im): no per-iteration host round trip
+ * (the reference fetches alpha/beta with .get() three times per iteration, :424,432,449).      */
+/* out[0..1] += sum conj(a)*b  (cMultiplyConjVec + reikna Reduce, :375-377,410-412) ; out must be
+ * zeroed by the caller (b200nufft_zero_scalars). */
+int b200nufft_dotc(const b200_c64* a, const b200_c64* b, int64_t n, double* out, void* stream);
+int b200nufft_zero_scalars(double* s, int n, void* stream);
+/* alpha = rsold/pAp ; x += alpha p ; r -= alpha Ap ; rsnew += sum conj(r) r   (:414-446) */
+int b200nufft_cg_update_xr(b200_c64* x, b200_c64* r, const b200_c64* p, const b200_c64* Ap,
+                           const double* rsold, const double* pAp, double* rsnew, int64_t n,
+                           void* stream);
+/* beta = rsnew/rsold ; p = r + beta p   (:448-455) */
+int b200nufft_cg_update_p(b200_c64* p, const b200_c64* r, const double* rsnew,
+                          const double* rsold, int64_t n, void* stream);
+/* r = b - Ax ; p = r ; rsold += sum conj(r) r   (:385-402) */
+int b200nufft_cg_init(const b200_c64* b, const b200_c64* Ax, b200_c64* r, b200_c64* p,
+                      double* rsold, int64_t n, void* stream);
+/* a[i] = a[i] / b[i] (complex) -- `k /= uker`, solve_device.py:178 */
+int b200nufft_cdiv(b200_c64* a, const b200_c64* b, int64_t n, void* stream);
+/* L1TVOLS, all arrays single-coil images of the plan's Nd (solve_device.py:74-275):
+ *   tv_rhs    : rhs = mu*AHyk + lambda * sum_p Dt_p(d_p - b_p)           (:133-154, cDiff :936-950)
+ *   tv_shrink : z_p = D_p(x); s_p = z_p + b_p; s = hypot chain + 1e-6; t = shrink(s,1/lambda)/s;
+ *               d_p = s_p t; b_p += z_p - d_p                               (:189-262, cHypot, cAnisoShrink)
+ *   tv_bregman: AHyk -= (zf - AHy)                                          (:196-198, :269)
+ * d and b are ndim arrays stored back to back: d_p at d + p*prod(Nd).                          */
+int b200nufft_tv_rhs(b200nufft_plan_t plan, const b200_c64* AHyk, const b200_c64* d,
+                     const b200_c64* b, float mu, float lambda, b200_c64* rhs, void* stream);
+int b200nufft_tv_shrink(b200nufft_plan_t plan, const b200_c64* x, b200_c64* d, b200_c64* b,
+                        float lambda, void* stream);
+int b200nufft_tv_bregman(b200_c64* AHyk, const b200_c64* zf, const b200_c64* AHy, int64_t n,
+                         void* stream);
+
+/* ---- tuning / introspection ---------------------------------------------------------------- */
+/* kernel variant selection: interp/gridding "auto" (0), "generic" (1), "tiled" (2) */
+int b200nufft_set_variant(b200nufft_plan_t plan, int interp_variant, int gridding_variant);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t b200nufft_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NUFFT_H */

@@ -246,23 +246,38 @@ class Plan:
 # --------------------------------------------------------------------------- #
 # bin / sort permutation contract (new in the B200 build)
 # --------------------------------------------------------------------------- #
-def bin_keys(k0, Kd, tile):
+def default_tiles(Kd):
+    """Tile / sub-tile edges the plan uses (csrc/plan.cu choose_tiles)."""
+    nd = len(Kd)
+    want = 16 if nd == 3 else (32 if nd == 2 else 256)
+    tile = tuple(min(want, k) for k in Kd)
+    sub = tuple(8 if (nd == 3 and t % 8 == 0) else t for t in tile)
+    return tile, sub
+
+
+def bin_keys(k0, Kd, tile, sub):
     """
-    key = C-order linear index of the tile that holds the first neighbour (k0+1) mod K.
-    k0: (M, d) integers from offset_k0 (bit-exact contract), tile: per-dim tile edge.
+    key = tile_linear * subtiles_per_tile + subtile_linear (both C-order) of the cell that holds
+    the first neighbour (k0+1) mod K.  k0: (M, d) integers from offset_k0 (bit-exact contract).
     """
     k0 = numpy.asarray(k0, dtype=numpy.int64)
     key = numpy.zeros(k0.shape[0], dtype=numpy.int64)
+    skey = numpy.zeros(k0.shape[0], dtype=numpy.int64)
+    nsubprod = 1
     for d in range(len(Kd)):
-        q = numpy.mod(k0[:, d] + 1, Kd[d]) // tile[d]
+        ks = numpy.mod(k0[:, d] + 1, Kd[d])
+        q = ks // tile[d]
         ntile = -(-Kd[d] // tile[d])
+        nsub = tile[d] // sub[d]
         key = key * ntile + q
-    return key
+        skey = skey * nsub + (ks - q * tile[d]) // sub[d]
+        nsubprod *= nsub
+    return key * nsubprod + skey
 
 
-def sort_permutation(k0, Kd, tile):
+def sort_permutation(k0, Kd, tile, sub):
     """Stable sort by bin key: the permutation the GPU plan must reproduce bit-exactly."""
-    return numpy.argsort(bin_keys(k0, Kd, tile), kind='stable')
+    return numpy.argsort(bin_keys(k0, Kd, tile, sub), kind='stable')
 
 
 # --------------------------------------------------------------------------- #

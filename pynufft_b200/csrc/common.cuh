@@ -1,0 +1,148 @@
+// Internal declarations shared by the translation units of libb200nufft.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nufft.h"
+
+#define MAXD B200NUFFT_MAX_DIM
+#define MAXJ B200NUFFT_MAX_J
+#define MAXL B200NUFFT_MAX_L
+
+enum {
+    B200_OK = 0,
+    B200_ERR_ARG = -1,
+    B200_ERR_CUDA = -2,
+    B200_ERR_CUFFT = -3,
+    B200_ERR_UNSUPPORTED = -4,
+};
+
+void b200_set_error(const std::string& msg);
+extern std::atomic<long long> g_launches;
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            b200_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +       \
+                           __FILE__ + ":" + std::to_string(__LINE__) + ")");                 \
+            return B200_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define CUFFT_TRY(expr)                                                                      \
+    do {                                                                                     \
+        cufftResult _e = (expr);                                                             \
+        if (_e != CUFFT_SUCCESS) {                                                           \
+            b200_set_error(std::string(#expr) + ": cufft error " + std::to_string((int)_e) + \
+                           " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")");          \
+            return B200_ERR_CUFFT;                                                           \
+        }                                                                                    \
+    } while (0)
+
+#define ARG_CHECK(cond, msg)                                                                 \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            b200_set_error(std::string("invalid argument: ") + msg);                         \
+            return B200_ERR_ARG;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                       \
+    do {                                                                                     \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
+        CUDA_TRY(cudaGetLastError());                                                        \
+    } while (0)
+
+// Geometry handed to kernels by value.
+struct Geom {
+    int ndim;
+    int N[MAXD];        // image size
+    int K[MAXD];        // oversampled grid size
+    int J[MAXD];        // interpolator width
+    int Joff[MAXD];     // prefix sum of J
+    int sumJ, prodJ;
+    int tile[MAXD];     // coarse bin (tile) edge per dim
+    int ntile[MAXD];    // tiles per dim
+    int sub[MAXD];      // sub-tile edge per dim (divides tile); the bin key is (tile, sub-tile)
+    int nsub[MAXD];     // sub-tiles per tile per dim
+    int nsubprod;       // sub-tiles per tile
+    int snoff[MAXD];    // offset of dim d inside the concatenated sn vector
+    long long Nprod, Kprod;
+    long long Kstride[MAXD];  // C-order element stride of the grid
+    int recw;           // words (4 B) per sample record, multiple of 4
+    float2 E[MAXD][MAXJ];     // E_d[j] = exp(+i gam_d (N_d-1)/2 (j+1)), j = 0..J_d-1
+};
+
+// Per-dimension float64 constants of the min-max interpolator (plan kernels only).
+struct PlanConst {
+    double gam[MAXD];           // 2 pi / K           (helper.py:905)
+    double ratio[MAXD];         // K / N              (helper.py:1093)
+    double alpha[MAXD][MAXL];   // alpha_|l|, l = 0..L
+    int L[MAXD];
+    double T[MAXD][MAXJ * MAXJ];// T_d row-major J x J (helper.py:1060-1083)
+};
+
+struct WorkItem {   // one launch unit of the tiled kernels: samples [begin, end) of one tile
+    int tile;
+    int begin;
+    int end;
+    int pad;
+};
+
+struct b200nufft_plan_s {
+    int device = 0;
+    Geom g;
+    PlanConst* d_pc = nullptr;      // device copy
+    long long M = 0;
+    int batch = 1;
+    // device buffers
+    double* d_om = nullptr;         // (M, ndim) original order
+    int* d_perm = nullptr;          // (M,)
+    float* d_rec = nullptr;         // (M, recw) sorted order
+    float* d_sn = nullptr;          // (sum N)
+    int* d_bin_start = nullptr;     // (n_bins + 1), n_bins = n_tiles * nsubprod
+    WorkItem* d_work = nullptr;
+    int n_work = 0;
+    int n_tiles = 0;
+    int n_bins = 0;
+    // scratch grids for the compositions
+    float2* d_grid = nullptr;
+    int grid_nb = 0;
+    // host staging for the *_host entry points
+    float2* d_xin = nullptr;
+    float2* d_yio = nullptr;
+    int io_nb = 0;
+    // cuFFT
+    cufftHandle fft = 0;
+    int fft_nb = 0;
+    bool fft_valid = false;
+    int interp_variant = 0, gridding_variant = 0;
+    long long bytes = 0;
+};
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// tiled kernels (interp_tiled.cu / grid_tiled.cu); return B200_ERR_UNSUPPORTED if geometry does not fit
+int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
+int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
+bool tiled_supported(const Geom& g);
+int ensure_scratch(b200nufft_plan_t p, int nb);
+
+// ---- small device helpers ---------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // conj(a) * b
+    return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ void cfma(float2& acc, float2 a, float2 b) {  // acc += a*b
+    acc.x = fmaf(a.x, b.x, acc.x);
+    acc.x = fmaf(-a.y, b.y, acc.x);
+    acc.y = fmaf(a.x, b.y, acc.y);
+    acc.y = fmaf(a.y, b.x, acc.y);
+}

@@ -1,0 +1,141 @@
+// Generic interpolation (gather) and gridding (scatter) kernels: any ndim <= 3, any J <= 16.
+// One warp per bin-sorted sample, lanes stride over the prod(J) neighbours, the tensor product
+// of the per-dimension factors is formed on the fly (as pELL_spmv_mCoil / pELL_spmvh_mCoil do,
+// src/re_subroutine.py:751-835, 527-596) but from real factors + constant phase tables held in
+// shared memory, with bin-sorted samples so neighbouring warps hit the same L2 lines.
+// These are the reference-shaped kernels; the tiled shared-memory kernels (interp_tiled.cu,
+// grid_tiled.cu) replace them for the geometries they support.
+#include "common.cuh"
+
+#define GEN_WARPS 8
+
+struct WarpFactors {
+    float2 a[MAXD * MAXJ];   // a_d[j] = c_d[j] * E_d[j]
+    int col[MAXD * MAXJ];    // wrapped index * stride
+};
+
+__device__ __forceinline__ void load_factors(const Geom& g, const float* __restrict__ r, WarpFactors& wf,
+                                             int lane) {
+    for (int t = lane; t < g.sumJ; t += 32) {
+        int d = 0;
+        if (g.ndim > 1 && t >= g.Joff[1]) d = 1;
+        if (g.ndim > 2 && t >= g.Joff[2]) d = 2;
+        int j = t - g.Joff[d];
+        float cv = r[t];
+        float2 E = g.E[d][j];
+        wf.a[t] = make_float2(cv * E.x, cv * E.y);
+        int ks = reinterpret_cast<const int*>(r)[g.sumJ + 2 + d];
+        int idx = ks + j;
+        if (idx >= g.K[d]) idx -= g.K[d];
+        wf.col[t] = (int)(idx * g.Kstride[d]);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void neighbour(const Geom& g, const WarpFactors& wf, int f, float2& w, int& col) {
+    // row-major decode of the flat neighbour id (meshindex, helper.py:376-383)
+    int t = g.Joff[g.ndim - 1] + f % g.J[g.ndim - 1];
+    w = wf.a[t];
+    col = wf.col[t];
+    f /= g.J[g.ndim - 1];
+    for (int d = g.ndim - 2; d >= 0; --d) {
+        t = g.Joff[d] + f % g.J[d];
+        f /= g.J[d];
+        w = cmul(w, wf.a[t]);
+        col += wf.col[t];
+    }
+}
+
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+k_interp_generic(Geom g, const float* __restrict__ rec, long long M, const float2* __restrict__ grid,
+                 float2* __restrict__ y, int nb) {
+    __shared__ WarpFactors swf[GEN_WARPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = blockIdx.x * (long long)GEN_WARPS + wib;
+    if (i >= M) return;
+    const int c = blockIdx.y;
+    const float* r = rec + i * g.recw;
+    WarpFactors& wf = swf[wib];
+    load_factors(g, r, wf, lane);
+    const float2* gc = grid + (long long)c * g.Kprod;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int f = lane; f < g.prodJ; f += 32) {
+        float2 w;
+        int col;
+        neighbour(g, wf, f, w, col);
+        cfma(acc, w, __ldg(gc + col));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (lane == 0) {
+        float2 P = make_float2(r[g.sumJ], r[g.sumJ + 1]);
+        int m = reinterpret_cast<const int*>(r)[g.sumJ + 2 + g.ndim];
+        y[(long long)m * nb + c] = cmul(P, acc);
+    }
+}
+
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+k_gridding_generic(Geom g, const float* __restrict__ rec, long long M, const float2* __restrict__ y,
+                   float2* __restrict__ grid, int nb) {
+    __shared__ WarpFactors swf[GEN_WARPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = blockIdx.x * (long long)GEN_WARPS + wib;
+    if (i >= M) return;
+    const int c = blockIdx.y;
+    const float* r = rec + i * g.recw;
+    WarpFactors& wf = swf[wib];
+    load_factors(g, r, wf, lane);
+    float2 P = make_float2(r[g.sumJ], r[g.sumJ + 1]);
+    int m = reinterpret_cast<const int*>(r)[g.sumJ + 2 + g.ndim];
+    float2 yv = cmulc(P, y[(long long)m * nb + c]);        // conj(P) * y
+    float2* gc = grid + (long long)c * g.Kprod;
+    for (int f = lane; f < g.prodJ; f += 32) {
+        float2 w;
+        int col;
+        neighbour(g, wf, f, w, col);
+        float2 v = cmulc(w, yv);                           // conj(w) * conj(P) * y
+        atomicAdd(gc + col, v);                            // REDG.E.ADD.F32x2
+    }
+}
+
+extern "C" int b200nufft_interp(b200nufft_plan_t p, const b200_c64* grid, b200_c64* y, int nb, void* stream) {
+    ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "interp: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (p->M == 0) return B200_OK;
+    cudaStream_t st = as_stream(stream);
+    if (p->interp_variant != 1 && tiled_supported(p->g)) {
+        return interp_tiled_launch(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, st);
+    }
+    if (p->interp_variant == 2) {
+        b200_set_error("interp: tiled variant requested but geometry unsupported");
+        return B200_ERR_UNSUPPORTED;
+    }
+    dim3 gr((unsigned)((p->M + GEN_WARPS - 1) / GEN_WARPS), nb);
+    k_interp_generic<<<gr, GEN_WARPS * 32, 0, st>>>(p->g, p->d_rec, p->M, reinterpret_cast<const float2*>(grid),
+                                                    reinterpret_cast<float2*>(y), nb);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {
+    ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "gridding: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = as_stream(stream);
+    CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
+    if (p->M == 0) return B200_OK;
+    if (p->gridding_variant != 1 && tiled_supported(p->g)) {
+        return gridding_tiled_launch(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, st);
+    }
+    if (p->gridding_variant == 2) {
+        b200_set_error("gridding: tiled variant requested but geometry unsupported");
+        return B200_ERR_UNSUPPORTED;
+    }
+    dim3 gr((unsigned)((p->M + GEN_WARPS - 1) / GEN_WARPS), nb);
+    k_gridding_generic<<<gr, GEN_WARPS * 32, 0, st>>>(p->g, p->d_rec, p->M, reinterpret_cast<const float2*>(y),
+                                                      reinterpret_cast<float2*>(grid), nb);
+    LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -1,0 +1,411 @@
+// Plan: per-sample min-max interpolator (float64), bin keys, stable sort, sample records.
+// Follows src/_helper/helper.py:148-210 (OMEGA_u, OMEGA_k), :606-618 (min_max), :900-907
+// (nufft_offset), :1086-1117 (nufft_r) of the reference; what is stored is new (per-dimension
+// REAL factors + one complex phase per sample instead of M x sum(J) complex values).
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+static thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+void b200_set_error(const std::string& msg) { g_err = msg; }
+
+extern "C" const char* b200nufft_last_error(void) { return g_err.c_str(); }
+extern "C" int b200nufft_version(void) { return 100; }
+extern "C" int64_t b200nufft_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// float64 per-(sample, dim) math
+// ------------------------------------------------------------------------------------------
+struct DimResult {
+    long long k0;      // floor(om/gam - J/2)                       (helper.py:905-906)
+    double dk;         // om/gam - k0                               (helper.py:1108)
+    double c[MAXJ];    // T . r                                     (helper.py:616)
+};
+
+__device__ __forceinline__ double np_sinc(double x) {  // numpy.sinc
+    double y = 3.141592653589793 * (x == 0.0 ? 1.0e-20 : x);
+    return sin(y) / y;
+}
+
+__device__ __forceinline__ long long offset_k0(double om, double gam, int J, double* q_out) {
+    // numpy: floor(1.0*om/gam - 1.0*J/2.0); explicit _rn ops forbid fma contraction
+    double q = __ddiv_rn(om, gam);
+    *q_out = q;
+    return (long long)floor(__dsub_rn(q, 0.5 * (double)J));
+}
+
+__device__ void dim_math(double om, int d, const Geom& g, const PlanConst* __restrict__ pc,
+                         DimResult& out) {
+    const int J = g.J[d];
+    const int L = pc->L[d];
+    double q;
+    long long k0 = offset_k0(om, pc->gam[d], J, &q);
+    double dk = __dsub_rn(q, (double)k0);
+    out.k0 = k0;
+    out.dk = dk;
+    const double ratio = pc->ratio[d];
+    double r[MAXJ];
+    for (int j = 0; j < J; ++j) {
+        double arg = -(double)(j + 1) + dk;           // outer_sum(-arange(1,J+1), dk)
+        double rr = 0.0;
+        for (int l = -L; l <= L; ++l) {               // same accumulation order as nufft_r
+            double a = pc->alpha[d][l < 0 ? -l : l];
+            rr = rr + a * np_sinc((arg + 1.0 * l) / ratio);   // beta == 1
+        }
+        r[j] = rr;
+    }
+    const double* T = pc->T[d];
+    for (int j1 = 0; j1 < J; ++j1) {
+        double s = 0.0;
+        for (int j2 = 0; j2 < J; ++j2) s += T[j1 * J + j2] * r[j2];
+        out.c[j1] = s;
+    }
+}
+
+__device__ __forceinline__ int wrap_index(long long v, int K) {  // numpy.mod for integers
+    long long m = v % K;
+    if (m < 0) m += K;
+    return (int)m;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_bin_keys(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om,
+                           long long M, int* __restrict__ keys, int* __restrict__ vals) {
+    long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    int key = 0, skey = 0;
+    for (int d = 0; d < g.ndim; ++d) {
+        double q;
+        long long k0 = offset_k0(om[m * g.ndim + d], pc->gam[d], g.J[d], &q);
+        int ks = wrap_index(k0 + 1, g.K[d]);
+        int t = ks / g.tile[d];
+        key = key * g.ntile[d] + t;
+        skey = skey * g.nsub[d] + (ks - t * g.tile[d]) / g.sub[d];
+    }
+    keys[m] = key * g.nsubprod + skey;
+    vals[m] = (int)m;
+}
+
+// one thread per sorted sample: gather om through perm, write the record
+// record words: [c_0[0..J0) | c_1 | c_2 | P.re P.im | kstart_0.. | perm | pad]
+__global__ void k_build_records(Geom g, const PlanConst* __restrict__ pc,
+                                const double* __restrict__ om, const int* __restrict__ perm,
+                                long long M, float* __restrict__ rec) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int m = perm[i];
+    float* out = rec + i * g.recw;
+    double pr = 1.0, pi = 0.0;
+    for (int d = 0; d < g.ndim; ++d) {
+        DimResult R;
+        double o = om[(long long)m * g.ndim + d];
+        dim_math(o, d, g, pc, R);
+        for (int j = 0; j < g.J[d]; ++j) out[g.Joff[d] + j] = (float)R.c[j];
+        // P_d = exp(i (om N/2 - gam (N-1)/2 dk))
+        double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+        double ph = o * (double)g.N[d] / 2.0 - s * R.dk;
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        double npr = pr * cs - pi * sn;
+        double npi = pr * sn + pi * cs;
+        pr = npr;
+        pi = npi;
+        reinterpret_cast<int*>(out)[g.sumJ + 2 + d] = wrap_index(R.k0 + 1, g.K[d]);
+    }
+    out[g.sumJ + 0] = (float)pr;
+    out[g.sumJ + 1] = (float)pi;
+    reinterpret_cast<int*>(out)[g.sumJ + 2 + g.ndim] = m;
+    for (int w = g.sumJ + 3 + g.ndim; w < g.recw; ++w) out[w] = 0.f;
+}
+
+__global__ void k_bin_start(const int* __restrict__ sorted_keys, long long M, int nbins,
+                             int* __restrict__ bin_start) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > nbins) return;
+    // lower_bound(sorted_keys, t)
+    long long lo = 0, hi = M;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    bin_start[t] = (int)lo;
+}
+
+// parity exports, original order, reference pELL layout (helper.py:346-393)
+__global__ void k_export(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om,
+                         long long M, uint32_t* __restrict__ kindx, float2* __restrict__ udata,
+                         int* __restrict__ k0out) {
+    long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    for (int d = 0; d < g.ndim; ++d) {
+        double o = om[m * g.ndim + d];
+        if (udata) {
+            DimResult R;
+            dim_math(o, d, g, pc, R);
+            double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+            for (int j = 0; j < g.J[d]; ++j) {
+                double arg = -(double)(j + 1) + R.dk;
+                double ph = o * (double)g.N[d] / 2.0 - s * arg;
+                double sn, cs;
+                sincos(ph, &sn, &cs);
+                udata[m * g.sumJ + g.Joff[d] + j] = make_float2((float)(R.c[j] * cs), (float)(R.c[j] * sn));
+            }
+        }
+        double q;
+        long long k0 = offset_k0(o, pc->gam[d], g.J[d], &q);
+        if (k0out) k0out[m * g.ndim + d] = (int)k0;
+        if (kindx) {
+            for (int j = 0; j < g.J[d]; ++j) {
+                long long idx = wrap_index(k0 + j + 1, g.K[d]);
+                kindx[m * g.sumJ + g.Joff[d] + j] = (uint32_t)(idx * g.Kstride[d]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static void choose_tiles(Geom& g) {
+    // tile edge per dim: the bin key of the sort contract.  3-D: 16^3 (staged box 21^3 for J=6),
+    // 2-D: 32^2, 1-D: 256; never larger than K.
+    // 3-D tiles are split into 8^3 sub-tiles (the gridding kernel's private boxes).
+    int want = g.ndim == 3 ? 16 : (g.ndim == 2 ? 32 : 256);
+    g.nsubprod = 1;
+    for (int d = 0; d < g.ndim; ++d) {
+        g.tile[d] = std::min(want, g.K[d]);
+        g.ntile[d] = (g.K[d] + g.tile[d] - 1) / g.tile[d];
+        g.sub[d] = (g.ndim == 3 && g.tile[d] % 8 == 0) ? 8 : g.tile[d];
+        g.nsub[d] = g.tile[d] / g.sub[d];
+        g.nsubprod *= g.nsub[d];
+    }
+}
+
+extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim,
+                                     const int32_t* Nd, const int32_t* Kd, const int32_t* Jd,
+                                     int64_t M, const double* om, int batch,
+                                     const double* alpha, const int32_t* alpha_len,
+                                     const double* Tmat, const float* sn, void* stream) {
+    ARG_CHECK(out != nullptr, "out is NULL");
+    ARG_CHECK(ndim >= 1 && ndim <= MAXD, "ndim must be 1..3");
+    ARG_CHECK(M >= 0 && M < (1LL << 31), "M out of range");
+    ARG_CHECK(batch >= 1, "batch must be >= 1");
+    ARG_CHECK(om != nullptr || M == 0, "om is NULL");
+    ARG_CHECK(alpha && alpha_len && Tmat && sn, "plan constants are NULL");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = as_stream(stream);
+
+    b200nufft_plan_s* p = new b200nufft_plan_s();
+    p->device = device;
+    p->M = M;
+    p->batch = batch;
+    Geom& g = p->g;
+    memset(&g, 0, sizeof(g));
+    g.ndim = ndim;
+    g.Nprod = 1;
+    g.Kprod = 1;
+    g.prodJ = 1;
+    int snsum = 0;
+    for (int d = 0; d < ndim; ++d) {
+        if (!(Nd[d] >= 1 && Kd[d] >= Nd[d] && Jd[d] >= 1 && Jd[d] <= MAXJ && Jd[d] <= Kd[d])) {
+            delete p;
+            b200_set_error("invalid argument: need 1 <= Nd <= Kd, 1 <= Jd <= min(16, Kd)");
+            return B200_ERR_ARG;
+        }
+        if (!(alpha_len[d] >= 1 && alpha_len[d] <= MAXL)) {
+            delete p;
+            b200_set_error("invalid argument: alpha_len out of range");
+            return B200_ERR_ARG;
+        }
+        g.N[d] = Nd[d];
+        g.K[d] = Kd[d];
+        g.J[d] = Jd[d];
+        g.Joff[d] = g.sumJ;
+        g.sumJ += Jd[d];
+        g.prodJ *= Jd[d];
+        g.snoff[d] = snsum;
+        snsum += Nd[d];
+        g.Nprod *= Nd[d];
+        g.Kprod *= Kd[d];
+    }
+    if (g.Kprod >= (1LL << 31)) {
+        delete p;
+        b200_set_error("invalid argument: prod(Kd) must be < 2^31");
+        return B200_ERR_ARG;
+    }
+    for (int d = ndim - 1; d >= 0; --d) {
+        g.Kstride[d] = (d == ndim - 1) ? 1 : g.Kstride[d + 1] * g.K[d + 1];
+    }
+    g.recw = ((g.sumJ + 2 + ndim + 1) + 3) & ~3;
+    choose_tiles(g);
+    p->n_tiles = 1;
+    for (int d = 0; d < ndim; ++d) p->n_tiles *= g.ntile[d];
+    p->n_bins = p->n_tiles * g.nsubprod;
+
+    PlanConst pc;
+    memset(&pc, 0, sizeof(pc));
+    for (int d = 0; d < ndim; ++d) {
+        pc.gam[d] = 2.0 * M_PI / ((double)g.K[d] * 1.0);
+        pc.ratio[d] = 1.0 * g.K[d] / g.N[d];
+        pc.L[d] = alpha_len[d] - 1;
+        for (int l = 0; l < alpha_len[d]; ++l) pc.alpha[d][l] = alpha[d * MAXL + l];
+        for (int i = 0; i < g.J[d] * g.J[d]; ++i) pc.T[d][i] = Tmat[d * MAXJ * MAXJ + i];
+        double s = pc.gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+        for (int j = 0; j < g.J[d]; ++j)
+            g.E[d][j] = make_float2((float)cos(s * (j + 1)), (float)sin(s * (j + 1)));
+    }
+
+#define PLAN_TRY(expr)                                                      \
+    do {                                                                    \
+        cudaError_t _e = (expr);                                            \
+        if (_e != cudaSuccess) {                                            \
+            b200_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+            b200nufft_plan_destroy(p);                                      \
+            return B200_ERR_CUDA;                                           \
+        }                                                                   \
+    } while (0)
+
+    const long long Mal = std::max<long long>(M, 1);
+    PLAN_TRY(cudaMalloc(&p->d_pc, sizeof(PlanConst)));
+    PLAN_TRY(cudaMemcpyAsync(p->d_pc, &pc, sizeof(pc), cudaMemcpyHostToDevice, st));
+    PLAN_TRY(cudaMalloc(&p->d_sn, sizeof(float) * snsum));
+    PLAN_TRY(cudaMemcpyAsync(p->d_sn, sn, sizeof(float) * snsum, cudaMemcpyDefault, st));
+    PLAN_TRY(cudaMalloc(&p->d_om, sizeof(double) * Mal * ndim));
+    if (M > 0) PLAN_TRY(cudaMemcpyAsync(p->d_om, om, sizeof(double) * M * ndim, cudaMemcpyDefault, st));
+    PLAN_TRY(cudaMalloc(&p->d_perm, sizeof(int) * Mal));
+    PLAN_TRY(cudaMalloc(&p->d_rec, sizeof(float) * Mal * g.recw));
+    PLAN_TRY(cudaMalloc(&p->d_bin_start, sizeof(int) * (p->n_bins + 1)));
+    p->bytes = sizeof(PlanConst) + sizeof(float) * snsum + sizeof(double) * Mal * ndim +
+               sizeof(int) * Mal + sizeof(float) * Mal * g.recw + sizeof(int) * (p->n_bins + 1);
+
+    std::vector<int> h_bin_start(p->n_bins + 1, 0);
+    if (M > 0) {
+        int *d_keys = nullptr, *d_keys_s = nullptr, *d_vals = nullptr;
+        void* d_tmp = nullptr;
+        PLAN_TRY(cudaMalloc(&d_keys, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&d_keys_s, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&d_vals, sizeof(int) * M));
+        const int TB = 256;
+        const unsigned nblk = (unsigned)((M + TB - 1) / TB);
+        k_bin_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, d_keys, d_vals);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        int end_bit = 1;
+        while ((1LL << end_bit) < p->n_bins) ++end_bit;
+        size_t tmp_bytes = 0;
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_perm,
+                                                 (int)M, 0, end_bit, st));
+        PLAN_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_perm,
+                                                 (int)M, 0, end_bit, st));   // stable LSD radix sort
+        k_bin_start<<<(p->n_bins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, p->n_bins, p->d_bin_start);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        k_build_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_rec);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        PLAN_TRY(cudaMemcpyAsync(h_bin_start.data(), p->d_bin_start, sizeof(int) * (p->n_bins + 1),
+                                 cudaMemcpyDeviceToHost, st));
+        PLAN_TRY(cudaStreamSynchronize(st));
+        cudaFree(d_keys);
+        cudaFree(d_keys_s);
+        cudaFree(d_vals);
+        cudaFree(d_tmp);
+    } else {
+        PLAN_TRY(cudaMemsetAsync(p->d_bin_start, 0, sizeof(int) * (p->n_bins + 1), st));
+        PLAN_TRY(cudaStreamSynchronize(st));
+    }
+
+    // work list for the tiled kernels: non-empty tiles, split into chunks, heaviest first
+    {
+        const int CHUNK = 1024;
+        std::vector<WorkItem> work;
+        for (int t = 0; t < p->n_tiles; ++t) {
+            int b = h_bin_start[t * g.nsubprod], e = h_bin_start[(t + 1) * g.nsubprod];
+            for (int s = b; s < e; s += CHUNK) work.push_back(WorkItem{t, s, std::min(e, s + CHUNK), 0});
+        }
+        std::stable_sort(work.begin(), work.end(), [](const WorkItem& a, const WorkItem& b) {
+            return (a.end - a.begin) > (b.end - b.begin);
+        });
+        p->n_work = (int)work.size();
+        if (p->n_work > 0) {
+            PLAN_TRY(cudaMalloc(&p->d_work, sizeof(WorkItem) * work.size()));
+            PLAN_TRY(cudaMemcpyAsync(p->d_work, work.data(), sizeof(WorkItem) * work.size(),
+                                     cudaMemcpyHostToDevice, st));
+            PLAN_TRY(cudaStreamSynchronize(st));
+            p->bytes += sizeof(WorkItem) * work.size();
+        }
+    }
+#undef PLAN_TRY
+    *out = p;
+    return B200_OK;
+}
+
+extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
+    if (!p) return B200_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_pc);
+    cudaFree(p->d_om);
+    cudaFree(p->d_perm);
+    cudaFree(p->d_rec);
+    cudaFree(p->d_sn);
+    cudaFree(p->d_bin_start);
+    cudaFree(p->d_work);
+    cudaFree(p->d_grid);
+    cudaFree(p->d_xin);
+    cudaFree(p->d_yio);
+    if (p->fft_valid) cufftDestroy(p->fft);
+    delete p;
+    return B200_OK;
+}
+
+static int run_export(b200nufft_plan_t p, uint32_t* kindx, float2* udata, int* k0, void* stream) {
+    ARG_CHECK(p != nullptr, "plan is NULL");
+    if (p->M == 0) return B200_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int TB = 128;
+    k_export<<<(unsigned)((p->M + TB - 1) / TB), TB, 0, as_stream(stream)>>>(p->g, p->d_pc, p->d_om, p->M,
+                                                                            kindx, udata, k0);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_plan_get_kindx(b200nufft_plan_t p, uint32_t* kindx, void* stream) {
+    return run_export(p, kindx, nullptr, nullptr, stream);
+}
+extern "C" int b200nufft_plan_get_udata(b200nufft_plan_t p, b200_c64* udata, void* stream) {
+    return run_export(p, nullptr, reinterpret_cast<float2*>(udata), nullptr, stream);
+}
+extern "C" int b200nufft_plan_get_k0(b200nufft_plan_t p, int32_t* k0, void* stream) {
+    return run_export(p, nullptr, nullptr, k0, stream);
+}
+extern "C" int b200nufft_plan_get_perm(b200nufft_plan_t p, int32_t* perm, void* stream) {
+    ARG_CHECK(p != nullptr, "plan is NULL");
+    if (p->M == 0) return B200_OK;
+    CUDA_TRY(cudaMemcpyAsync(perm, p->d_perm, sizeof(int) * p->M, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return B200_OK;
+}
+extern "C" int b200nufft_plan_get_tile(b200nufft_plan_t p, int32_t* tile_host) {
+    ARG_CHECK(p != nullptr, "plan is NULL");
+    for (int d = 0; d < p->g.ndim; ++d) {
+        tile_host[d] = p->g.tile[d];
+        tile_host[p->g.ndim + d] = p->g.sub[d];
+    }
+    return B200_OK;
+}
+extern "C" int64_t b200nufft_plan_bytes(b200nufft_plan_t p) { return p ? p->bytes : 0; }
+
+extern "C" int b200nufft_set_variant(b200nufft_plan_t p, int iv, int gv) {
+    ARG_CHECK(p != nullptr, "plan is NULL");
+    ARG_CHECK(iv >= 0 && iv <= 2 && gv >= 0 && gv <= 2, "variant must be 0..2");
+    p->interp_variant = iv;
+    p->gridding_variant = gv;
+    return B200_OK;
+}

@@ -1,0 +1,311 @@
+// Fused vector kernels for the device solvers (linalg/solve_device.py:351-481 CG, :74-275
+// L1TVOLS).  The reference launches cMultiplyConjVec / cMultiplyScalar / cAddVec / cDiff / cHypot /
+// cAnisoShrink / cMultiplyVec (src/re_subroutine.py) plus reikna array arithmetic one pass at a
+// time and fetches alpha/beta to the host each iteration; here every CG step is two streaming
+// kernels and the scalars never leave the device.
+#include "common.cuh"
+
+#define RED_TB 256
+#define RED_BLOCKS (148 * 4)
+
+__device__ __forceinline__ void block_reduce_add2(double re, double im, double* out) {
+    __shared__ double sre[RED_TB / 32], sim[RED_TB / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sre[w] = re; sim[w] = im; }
+    __syncthreads();
+    if (w == 0) {
+        re = l < RED_TB / 32 ? sre[l] : 0.0;
+        im = l < RED_TB / 32 ? sim[l] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, o);
+            im += __shfl_xor_sync(0xffffffffu, im, o);
+        }
+        if (l == 0) {
+            atomicAdd(out, re);
+            atomicAdd(out + 1, im);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RED_TB) k_dotc(const float2* __restrict__ a, const float2* __restrict__ b,
+                                                 long long n, double* __restrict__ out) {
+    float re = 0.f, im = 0.f;
+    double dre = 0.0, dim_ = 0.0;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int cnt = 0;
+    for (; i < n; i += stride) {
+        float2 x = a[i], y = b[i];
+        re = fmaf(x.x, y.x, fmaf(x.y, y.y, re));
+        im = fmaf(x.x, y.y, fmaf(-x.y, y.x, im));
+        if (++cnt == 64) { dre += re; dim_ += im; re = im = 0.f; cnt = 0; }   // bounded f32 partials
+    }
+    dre += re;
+    dim_ += im;
+    block_reduce_add2(dre, dim_, out);
+}
+
+__device__ __forceinline__ float2 cdivd(const double* num, const double* den) {  // (double) num/den -> c64
+    double a = num[0], b = num[1], c = den[0], d = den[1];
+    double m = c * c + d * d;
+    return make_float2((float)((a * c + b * d) / m), (float)((b * c - a * d) / m));
+}
+
+__global__ void __launch_bounds__(RED_TB)
+k_cg_init(const float2* __restrict__ b, const float2* __restrict__ Ax, float2* __restrict__ r,
+          float2* __restrict__ p, double* __restrict__ rsold, long long n) {
+    double dre = 0.0;
+    float re = 0.f;
+    int cnt = 0;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 bv = b[i], av = Ax[i];
+        float2 rv = make_float2(bv.x - av.x, bv.y - av.y);
+        r[i] = rv;
+        p[i] = rv;
+        re = fmaf(rv.x, rv.x, fmaf(rv.y, rv.y, re));
+        if (++cnt == 64) { dre += re; re = 0.f; cnt = 0; }
+    }
+    dre += re;
+    block_reduce_add2(dre, 0.0, rsold);
+}
+
+__global__ void __launch_bounds__(RED_TB)
+k_cg_update_xr(float2* __restrict__ x, float2* __restrict__ r, const float2* __restrict__ p,
+               const float2* __restrict__ Ap, const double* __restrict__ rsold, const double* __restrict__ pAp,
+               double* __restrict__ rsnew, long long n) {
+    const float2 alpha = cdivd(rsold, pAp);
+    double dre = 0.0;
+    float re = 0.f;
+    int cnt = 0;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 pv = p[i], qv = Ap[i], xv = x[i], rv = r[i];
+        float2 ap = cmul(alpha, pv), aq = cmul(alpha, qv);
+        xv.x += ap.x; xv.y += ap.y;
+        rv.x -= aq.x; rv.y -= aq.y;
+        x[i] = xv;
+        r[i] = rv;
+        re = fmaf(rv.x, rv.x, fmaf(rv.y, rv.y, re));
+        if (++cnt == 64) { dre += re; re = 0.f; cnt = 0; }
+    }
+    dre += re;
+    block_reduce_add2(dre, 0.0, rsnew);
+}
+
+__global__ void k_cg_update_p(float2* __restrict__ p, const float2* __restrict__ r,
+                              const double* __restrict__ rsnew, const double* __restrict__ rsold, long long n) {
+    const float2 beta = cdivd(rsnew, rsold);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 bp = cmul(beta, p[i]);
+        float2 rv = r[i];
+        p[i] = make_float2(rv.x + bp.x, rv.y + bp.y);
+    }
+}
+
+__global__ void k_cdiv(float2* __restrict__ a, const float2* __restrict__ b, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 x = a[i], y = b[i];
+        float m = y.x * y.x + y.y * y.y;
+        a[i] = make_float2((x.x * y.x + x.y * y.y) / m, (x.y * y.x - x.x * y.y) / m);
+    }
+}
+
+// ---- L1TVOLS ---------------------------------------------------------------------------------
+// periodic neighbour along axis d of the linear image index n
+__device__ __forceinline__ long long shifted(const Geom& g, long long n, int d, int step, const int* coord,
+                                             const long long* nstride) {
+    int i = coord[d] + step;
+    if (i < 0) i += g.N[d];
+    if (i >= g.N[d]) i -= g.N[d];
+    return n + (long long)(i - coord[d]) * nstride[d];
+}
+
+__device__ __forceinline__ void decode_image(const Geom& g, long long n, int* coord, long long* nstride) {
+    long long s = g.Nprod;
+    for (int d = 0; d < g.ndim; ++d) {
+        s /= g.N[d];
+        nstride[d] = s;
+        coord[d] = (int)(n / s);
+        n -= coord[d] * s;
+    }
+}
+
+// rhs = mu*AHyk + lambda * sum_p Dt_p(d_p - b_p),  Dt_p(v)[i] = v[i + e_p] - v[i]
+// (solve_device.py:133-154; dt_indx = roll(-1), helper.py:67; cDiff re_subroutine.py:936-950)
+__global__ void k_tv_rhs(Geom g, const float2* __restrict__ AHyk, const float2* __restrict__ dd,
+                         const float2* __restrict__ bb, float mu, float lambda, float2* __restrict__ rhs) {
+    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= g.Nprod) return;
+    int coord[MAXD];
+    long long ns[MAXD];
+    decode_image(g, n, coord, ns);
+    float2 a = AHyk[n];
+    float2 acc = make_float2(mu * a.x, mu * a.y);
+    for (int p = 0; p < g.ndim; ++p) {
+        const float2* dp = dd + (long long)p * g.Nprod;
+        const float2* bp = bb + (long long)p * g.Nprod;
+        long long nn = shifted(g, n, p, +1, coord, ns);
+        float2 v1 = make_float2(dp[nn].x - bp[nn].x, dp[nn].y - bp[nn].y);
+        float2 v0 = make_float2(dp[n].x - bp[n].x, dp[n].y - bp[n].y);
+        float2 t = make_float2((v1.x - v0.x) * lambda, (v1.y - v0.y) * lambda);
+        acc.x += t.x;
+        acc.y += t.y;
+    }
+    rhs[n] = acc;
+}
+
+// z_p = D_p(x) (D_p(v)[i] = v[i - e_p] - v[i]; d_indx = roll(+1), helper.py:66); s_p = z_p + b_p;
+// s = s_0, then hypot(|s|,|s_p|) (cHypot :656-678); s += 1e-6; t = shrink(s, 1/lambda)/s
+// (cAnisoShrink :973-993); d_p = s_p*t; b_p += z_p - d_p          (solve_device.py:189-262)
+__global__ void k_tv_shrink(Geom g, const float2* __restrict__ x, float2* __restrict__ dd,
+                            float2* __restrict__ bb, float lambda) {
+    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= g.Nprod) return;
+    int coord[MAXD];
+    long long ns[MAXD];
+    decode_image(g, n, coord, ns);
+    const float2 x0 = x[n];
+    float2 z[MAXD], sp[MAXD];
+    float2 s = make_float2(0.f, 0.f);
+    for (int p = 0; p < g.ndim; ++p) {
+        float2 xm = x[shifted(g, n, p, -1, coord, ns)];
+        z[p] = make_float2(xm.x - x0.x, xm.y - x0.y);
+        float2 b = bb[(long long)p * g.Nprod + n];
+        sp[p] = make_float2(z[p].x + b.x, z[p].y + b.y);
+        if (p == 0) {
+            s = sp[0];
+        } else {
+            float hx = hypotf(s.x, s.y), hy = hypotf(sp[p].x, sp[p].y);
+            s = make_float2(hypotf(hx, hy), 0.f);
+        }
+    }
+    s.x += 1e-6f;
+    const float thr = 1.0f / lambda;
+    float2 t;
+    t.x = (s.x > thr) * (s.x - thr) + (s.x < -thr) * (s.x + thr);
+    t.y = (s.y > thr) * (s.y - thr) + (s.y < -thr) * (s.y + thr);
+    {   // t /= s (complex)
+        float m = s.x * s.x + s.y * s.y;
+        t = make_float2((t.x * s.x + t.y * s.y) / m, (t.y * s.x - t.x * s.y) / m);
+    }
+    for (int p = 0; p < g.ndim; ++p) {
+        float2 d = cmul(sp[p], t);
+        long long o = (long long)p * g.Nprod + n;
+        float2 b = bb[o];
+        dd[o] = d;
+        bb[o] = make_float2(b.x + (z[p].x - d.x), b.y + (z[p].y - d.y));
+    }
+}
+
+__global__ void k_tv_bregman(float2* __restrict__ AHyk, const float2* __restrict__ zf,
+                             const float2* __restrict__ AHy, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 a = AHyk[i], z = zf[i], h = AHy[i];
+        AHyk[i] = make_float2(a.x - (z.x - h.x), a.y - (z.y - h.y));
+    }
+}
+
+// ---- C ABI -------------------------------------------------------------------------------------
+static inline unsigned stream_blocks(long long n) {
+    long long b = (n + RED_TB - 1) / RED_TB;
+    return (unsigned)(b < RED_BLOCKS ? (b > 0 ? b : 1) : RED_BLOCKS);
+}
+
+extern "C" int b200nufft_zero_scalars(double* s, int n, void* stream) {
+    ARG_CHECK(s && n >= 0, "zero_scalars: bad arguments");
+    CUDA_TRY(cudaMemsetAsync(s, 0, sizeof(double) * n, as_stream(stream)));
+    return B200_OK;
+}
+
+extern "C" int b200nufft_dotc(const b200_c64* a, const b200_c64* b, int64_t n, double* out, void* stream) {
+    ARG_CHECK(a && b && out && n >= 0, "dotc: bad arguments");
+    k_dotc<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(a),
+                                                               reinterpret_cast<const float2*>(b), n, out);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_cg_init(const b200_c64* b, const b200_c64* Ax, b200_c64* r, b200_c64* p, double* rsold,
+                                 int64_t n, void* stream) {
+    ARG_CHECK(b && Ax && r && p && rsold && n >= 0, "cg_init: bad arguments");
+    k_cg_init<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float2*>(b), reinterpret_cast<const float2*>(Ax), reinterpret_cast<float2*>(r),
+        reinterpret_cast<float2*>(p), rsold, n);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_cg_update_xr(b200_c64* x, b200_c64* r, const b200_c64* p, const b200_c64* Ap,
+                                      const double* rsold, const double* pAp, double* rsnew, int64_t n,
+                                      void* stream) {
+    ARG_CHECK(x && r && p && Ap && rsold && pAp && rsnew && n >= 0, "cg_update_xr: bad arguments");
+    k_cg_update_xr<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
+        reinterpret_cast<float2*>(x), reinterpret_cast<float2*>(r), reinterpret_cast<const float2*>(p),
+        reinterpret_cast<const float2*>(Ap), rsold, pAp, rsnew, n);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_cg_update_p(b200_c64* p, const b200_c64* r, const double* rsnew, const double* rsold,
+                                     int64_t n, void* stream) {
+    ARG_CHECK(p && r && rsnew && rsold && n >= 0, "cg_update_p: bad arguments");
+    k_cg_update_p<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
+        reinterpret_cast<float2*>(p), reinterpret_cast<const float2*>(r), rsnew, rsold, n);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_cdiv(b200_c64* a, const b200_c64* b, int64_t n, void* stream) {
+    ARG_CHECK(a && b && n >= 0, "cdiv: bad arguments");
+    k_cdiv<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(a),
+                                                               reinterpret_cast<const float2*>(b), n);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_tv_rhs(b200nufft_plan_t p, const b200_c64* AHyk, const b200_c64* d, const b200_c64* b,
+                                float mu, float lambda, b200_c64* rhs, void* stream) {
+    ARG_CHECK(p && AHyk && d && b && rhs, "tv_rhs: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int TB = 256;
+    k_tv_rhs<<<(unsigned)((p->g.Nprod + TB - 1) / TB), TB, 0, as_stream(stream)>>>(
+        p->g, reinterpret_cast<const float2*>(AHyk), reinterpret_cast<const float2*>(d),
+        reinterpret_cast<const float2*>(b), mu, lambda, reinterpret_cast<float2*>(rhs));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_tv_shrink(b200nufft_plan_t p, const b200_c64* x, b200_c64* d, b200_c64* b, float lambda,
+                                   void* stream) {
+    ARG_CHECK(p && x && d && b && lambda != 0.f, "tv_shrink: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int TB = 256;
+    k_tv_shrink<<<(unsigned)((p->g.Nprod + TB - 1) / TB), TB, 0, as_stream(stream)>>>(
+        p->g, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(d), reinterpret_cast<float2*>(b), lambda);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_tv_bregman(b200_c64* AHyk, const b200_c64* zf, const b200_c64* AHy, int64_t n,
+                                    void* stream) {
+    ARG_CHECK(AHyk && zf && AHy && n >= 0, "tv_bregman: bad arguments");
+    k_tv_bregman<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
+        reinterpret_cast<float2*>(AHyk), reinterpret_cast<const float2*>(zf), reinterpret_cast<const float2*>(AHy), n);
+    LAUNCH_CHECK();
+    return B200_OK;
+}

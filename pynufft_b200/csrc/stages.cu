@@ -1,0 +1,340 @@
+// Scaling / zero-padding / cropping kernels, cuFFT wrapper, operator compositions.
+// Replaces cTensorMultiply, cTensorCopy, cPopulate, cMultiplyVecInplace,
+// cMultiplyConjVecInplace, cAggregate (src/re_subroutine.py:98-201, 441-514, 839-921) and the
+// reikna FFT (nufft/_nufft_class_methods_device.py:246-249).
+#include <algorithm>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// x2xx: out = in * sn or in / sn   (image layout, batch innermost)
+// ------------------------------------------------------------------------------------------
+__global__ void k_x2xx(Geom g, const float* __restrict__ sn, const float2* __restrict__ in,
+                       float2* __restrict__ out, int nb, int div) {
+    long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (gid >= g.Nprod * nb) return;
+    long long n = gid / nb;
+    // same factor order as cTensorMultiply (re_subroutine.py:169-178): dim 0 first
+    float s = 1.f;
+    {
+        long long res = n;
+        long long stride = g.Nprod;
+        for (int d = 0; d < g.ndim; ++d) {
+            stride /= g.N[d];
+            int i = (int)(res / stride);
+            res -= i * stride;
+            s = s * sn[g.snoff[d] + i];
+        }
+    }
+    float2 v = in[gid];
+    if (div) { v.x = v.x / s; v.y = v.y / s; } else { v.x *= s; v.y *= s; }
+    out[gid] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// scale_pad: one thread per PAIR of grid elements along the last axis (float4 store) when the
+// last extents are even, else one element per thread.  blockIdx.y = coil.
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void k_scale_pad(Geom g, const float* __restrict__ sn, const float2* __restrict__ x,
+                            float2* __restrict__ grid, int nb, int apply_sn, int x_single,
+                            const float2* __restrict__ sens) {
+    const int c = blockIdx.y;
+    long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * VEC;
+    if (e >= g.Kprod) return;
+    // decode grid index -> image index; inside iff every coordinate < N_d
+    const int dl = g.ndim - 1;
+    long long rem = e;
+    long long n = 0;
+    bool inside = true;
+    float sbase = 1.f;
+    long long nstride = g.Nprod;
+    for (int d = 0; d < dl; ++d) {
+        nstride /= g.N[d];
+        int i = (int)(rem / g.Kstride[d]);
+        rem -= i * g.Kstride[d];
+        if (i >= g.N[d]) {
+            inside = false;
+        } else {
+            n += i * nstride;
+            if (apply_sn) sbase *= sn[g.snoff[d] + i];
+        }
+    }
+    const int ilast = (int)rem;
+    float2 v[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) v[q] = make_float2(0.f, 0.f);
+    if (inside) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            if (ilast + q < g.N[dl]) {
+                long long nn = n + ilast + q;
+                float2 xv = x_single ? x[nn] : x[nn * nb + c];
+                if (sens) xv = cmul(xv, sens[nn * nb + c]);
+                float f = apply_sn ? sbase * sn[g.snoff[dl] + ilast + q] : 1.f;
+                v[q] = make_float2(xv.x * f, xv.y * f);
+            }
+        }
+    }
+    float2* dst = grid + (long long)c * g.Kprod + e;
+    if (VEC == 2) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0].x, v[0].y, v[VEC - 1].x, v[VEC - 1].y);
+    } else {
+        dst[0] = v[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// crop_scale
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long image_to_grid(const Geom& g, long long n, float* s_out,
+                                                   const float* __restrict__ sn) {
+    long long idx = 0;
+    float s = 1.f;
+    long long nstride = g.Nprod;
+    for (int d = 0; d < g.ndim; ++d) {
+        nstride /= g.N[d];
+        int i = (int)(n / nstride);
+        n -= i * nstride;
+        idx += i * g.Kstride[d];
+        s *= sn[g.snoff[d] + i];
+    }
+    *s_out = s;
+    return idx;
+}
+
+__global__ void k_crop_scale(Geom g, const float* __restrict__ sn, const float2* __restrict__ grid,
+                             float2* __restrict__ x, int nb, int mode, float scale) {
+    long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (gid >= g.Nprod * nb) return;
+    long long n = gid / nb;
+    int c = (int)(gid - n * nb);
+    float s;
+    long long idx = image_to_grid(g, n, &s, sn);
+    float f = scale * (mode == 1 ? s : (mode == 2 ? 1.f / s : 1.f));
+    float2 v = grid[(long long)c * g.Kprod + idx];
+    x[gid] = make_float2(v.x * f, v.y * f);
+}
+
+__global__ void k_crop_combine(Geom g, const float* __restrict__ sn, const float2* __restrict__ grid,
+                               float2* __restrict__ x, int nb, int mode, float scale,
+                               const float2* __restrict__ sens) {
+    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= g.Nprod) return;
+    float s;
+    long long idx = image_to_grid(g, n, &s, sn);
+    float f = scale * (mode == 1 ? s : (mode == 2 ? 1.f / s : 1.f)) / (float)nb;   // mean over coils
+    float2 acc = make_float2(0.f, 0.f);
+    for (int c = 0; c < nb; ++c) {
+        float2 v = grid[(long long)c * g.Kprod + idx];
+        if (sens) v = cmulc(sens[n * nb + c], v);
+        acc.x += v.x;
+        acc.y += v.y;
+    }
+    x[n] = make_float2(acc.x * f, acc.y * f);
+}
+
+__global__ void k_scale_inplace(float2* __restrict__ a, long long n, float f) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 v = a[i];
+        a[i] = make_float2(v.x * f, v.y * f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int b200nufft_x2xx(b200nufft_plan_t p, const b200_c64* in, b200_c64* out, int nb, int div,
+                              void* stream) {
+    ARG_CHECK(p && in && out && nb >= 1, "x2xx: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    long long tot = p->g.Nprod * nb;
+    const int TB = 256;
+    k_x2xx<<<(unsigned)((tot + TB - 1) / TB), TB, 0, as_stream(stream)>>>(
+        p->g, p->d_sn, reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), nb, div);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_scale_pad(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb,
+                                   int apply_sn, int x_single, const b200_c64* sens, void* stream) {
+    ARG_CHECK(p && x && grid && nb >= 1 && nb <= 65535, "scale_pad: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const Geom& g = p->g;
+    const int TB = 256;
+    const int dl = g.ndim - 1;
+    bool vec2 = (g.K[dl] % 2 == 0) && (g.N[dl] % 2 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+    if (vec2) {
+        long long nthr = g.Kprod / 2;
+        dim3 gr((unsigned)((nthr + TB - 1) / TB), nb);
+        k_scale_pad<2><<<gr, TB, 0, as_stream(stream)>>>(g, p->d_sn, reinterpret_cast<const float2*>(x),
+                                                         reinterpret_cast<float2*>(grid), nb, apply_sn, x_single,
+                                                         reinterpret_cast<const float2*>(sens));
+    } else {
+        dim3 gr((unsigned)((g.Kprod + TB - 1) / TB), nb);
+        k_scale_pad<1><<<gr, TB, 0, as_stream(stream)>>>(g, p->d_sn, reinterpret_cast<const float2*>(x),
+                                                         reinterpret_cast<float2*>(grid), nb, apply_sn, x_single,
+                                                         reinterpret_cast<const float2*>(sens));
+    }
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+static int get_fft(b200nufft_plan_t p, int nb, cufftHandle* out) {
+    if (p->fft_valid && p->fft_nb == nb) { *out = p->fft; return B200_OK; }
+    if (p->fft_valid) { cufftDestroy(p->fft); p->fft_valid = false; }
+    int n[MAXD];
+    for (int d = 0; d < p->g.ndim; ++d) n[d] = p->g.K[d];
+    CUFFT_TRY(cufftPlanMany(&p->fft, p->g.ndim, n, nullptr, 1, (int)p->g.Kprod, nullptr, 1, (int)p->g.Kprod,
+                            CUFFT_C2C, nb));
+    p->fft_valid = true;
+    p->fft_nb = nb;
+    *out = p->fft;
+    return B200_OK;
+}
+
+// inverse: 0 forward, 1 inverse normalised by 1/prod(Kd), 2 inverse unnormalised
+extern "C" int b200nufft_fft(b200nufft_plan_t p, b200_c64* grid, int nb, int inverse, void* stream) {
+    ARG_CHECK(p && grid && nb >= 1, "fft: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    cufftHandle h;
+    int rc = get_fft(p, nb, &h);
+    if (rc) return rc;
+    CUFFT_TRY(cufftSetStream(h, as_stream(stream)));
+    CUFFT_TRY(cufftExecC2C(h, reinterpret_cast<cufftComplex*>(grid), reinterpret_cast<cufftComplex*>(grid),
+                           inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
+    if (inverse == 1) {
+        long long tot = p->g.Kprod * nb;
+        k_scale_inplace<<<148 * 8, 256, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(grid), tot,
+                                                               1.0f / (float)p->g.Kprod);
+        LAUNCH_CHECK();
+    }
+    return B200_OK;
+}
+
+static int crop_scale_impl(b200nufft_plan_t p, const float2* grid, float2* x, int nb, int mode, int combine,
+                           const float2* sens, float scale, cudaStream_t st) {
+    const int TB = 256;
+    if (combine) {
+        k_crop_combine<<<(unsigned)((p->g.Nprod + TB - 1) / TB), TB, 0, st>>>(p->g, p->d_sn, grid, x, nb, mode,
+                                                                             scale, sens);
+    } else {
+        long long tot = p->g.Nprod * nb;
+        k_crop_scale<<<(unsigned)((tot + TB - 1) / TB), TB, 0, st>>>(p->g, p->d_sn, grid, x, nb, mode, scale);
+    }
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_crop_scale(b200nufft_plan_t p, const b200_c64* grid, b200_c64* x, int nb, int mode,
+                                    int combine, const b200_c64* sens, void* stream) {
+    ARG_CHECK(p && grid && x && nb >= 1 && mode >= 0 && mode <= 2, "crop_scale: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return crop_scale_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(x), nb, mode,
+                           combine, reinterpret_cast<const float2*>(sens), 1.0f, as_stream(stream));
+}
+
+int ensure_scratch(b200nufft_plan_t p, int nb) {
+    if (p->grid_nb >= nb) return B200_OK;
+    if (p->d_grid) { CUDA_TRY(cudaFree(p->d_grid)); p->d_grid = nullptr; p->grid_nb = 0; }
+    CUDA_TRY(cudaMalloc(&p->d_grid, sizeof(float2) * p->g.Kprod * nb));
+    p->grid_nb = nb;
+    return B200_OK;
+}
+
+static int forward_impl(b200nufft_plan_t p, const float2* x, int x_single, const float2* sens, float2* y, int nb,
+                        void* stream) {
+    int rc = ensure_scratch(p, nb);
+    if (rc) return rc;
+    rc = b200nufft_scale_pad(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
+                             x_single, reinterpret_cast<const b200_c64*>(sens), stream);
+    if (rc) return rc;
+    rc = b200nufft_fft(p, reinterpret_cast<b200_c64*>(p->d_grid), nb, 0, stream);
+    if (rc) return rc;
+    return b200nufft_interp(p, reinterpret_cast<const b200_c64*>(p->d_grid), reinterpret_cast<b200_c64*>(y), nb,
+                            stream);
+}
+
+static int adjoint_impl(b200nufft_plan_t p, const float2* y, float2* x, int nb, int combine, const float2* sens,
+                        void* stream) {
+    int rc = ensure_scratch(p, nb);
+    if (rc) return rc;
+    rc = b200nufft_gridding(p, reinterpret_cast<const b200_c64*>(y), reinterpret_cast<b200_c64*>(p->d_grid), nb,
+                            stream);
+    if (rc) return rc;
+    rc = b200nufft_fft(p, reinterpret_cast<b200_c64*>(p->d_grid), nb, 2, stream);
+    if (rc) return rc;
+    // the 1/prod(Kd) of the inverse FFT is folded into the crop kernel
+    return crop_scale_impl(p, p->d_grid, x, nb, 1, combine, sens, 1.0f / (float)p->g.Kprod, as_stream(stream));
+}
+
+extern "C" int b200nufft_forward(b200nufft_plan_t p, const b200_c64* x, b200_c64* y, int nb, void* stream) {
+    ARG_CHECK(p && x && y && nb >= 1, "forward: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return forward_impl(p, reinterpret_cast<const float2*>(x), 0, nullptr, reinterpret_cast<float2*>(y), nb, stream);
+}
+
+extern "C" int b200nufft_adjoint(b200nufft_plan_t p, const b200_c64* y, b200_c64* x, int nb, void* stream) {
+    ARG_CHECK(p && x && y && nb >= 1, "adjoint: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return adjoint_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(x), nb, 0, nullptr, stream);
+}
+
+extern "C" int b200nufft_forward_one2many(b200nufft_plan_t p, const b200_c64* s, const b200_c64* sens,
+                                          b200_c64* y, int nb, void* stream) {
+    ARG_CHECK(p && s && y && nb >= 1, "forward_one2many: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return forward_impl(p, reinterpret_cast<const float2*>(s), 1, reinterpret_cast<const float2*>(sens),
+                        reinterpret_cast<float2*>(y), nb, stream);
+}
+
+extern "C" int b200nufft_adjoint_many2one(b200nufft_plan_t p, const b200_c64* y, const b200_c64* sens,
+                                          b200_c64* s, int nb, void* stream) {
+    ARG_CHECK(p && s && y && nb >= 1, "adjoint_many2one: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return adjoint_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(s), nb, 1,
+                        reinterpret_cast<const float2*>(sens), stream);
+}
+
+static int ensure_io(b200nufft_plan_t p, int nb) {
+    if (p->io_nb >= nb) return B200_OK;
+    if (p->d_xin) { cudaFree(p->d_xin); p->d_xin = nullptr; }
+    if (p->d_yio) { cudaFree(p->d_yio); p->d_yio = nullptr; }
+    p->io_nb = 0;
+    CUDA_TRY(cudaMalloc(&p->d_xin, sizeof(float2) * p->g.Nprod * nb));
+    CUDA_TRY(cudaMalloc(&p->d_yio, sizeof(float2) * std::max<long long>(p->M, 1) * nb));
+    p->io_nb = nb;
+    return B200_OK;
+}
+
+extern "C" int b200nufft_forward_host(b200nufft_plan_t p, const b200_c64* x_host, b200_c64* y_host, int nb,
+                                      void* stream) {
+    ARG_CHECK(p && x_host && y_host && nb >= 1, "forward_host: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = ensure_io(p, nb);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    CUDA_TRY(cudaMemcpyAsync(p->d_xin, x_host, sizeof(float2) * p->g.Nprod * nb, cudaMemcpyHostToDevice, st));
+    rc = forward_impl(p, p->d_xin, 0, nullptr, p->d_yio, nb, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(y_host, p->d_yio, sizeof(float2) * p->M * nb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200nufft_adjoint_host(b200nufft_plan_t p, const b200_c64* y_host, b200_c64* x_host, int nb,
+                                      void* stream) {
+    ARG_CHECK(p && x_host && y_host && nb >= 1, "adjoint_host: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = ensure_io(p, nb);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    CUDA_TRY(cudaMemcpyAsync(p->d_yio, y_host, sizeof(float2) * p->M * nb, cudaMemcpyHostToDevice, st));
+    rc = adjoint_impl(p, p->d_yio, p->d_xin, nb, 0, nullptr, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(x_host, p->d_xin, sizeof(float2) * p->g.Nprod * nb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}

@@ -1,0 +1,401 @@
+"""
+class NUFFT -- the reference operator API (nufft/__init__.py:496-739 `class NUFFT`, batch API from
+linalg/nufft_hsa.py `class NUFFT_hsa`) driven through libb200nufft.so.
+
+Method names, argument meaning, return values and error behaviour follow the reference:
+  plan(om, Nd, Kd, Jd, ft_axes=None, batch=None, radix=None) -> 0
+  forward / adjoint / selfadjoint / solve and the stage methods x2xx, xx2k, k2y, y2k, k2xx, xx2x
+      take and return numpy arrays (the reference's `_host` wrappers,
+      nufft/_nufft_class_methods_cpu.py:366-445)
+  _forward_device / _adjoint_device / _selfadjoint_device / _x2xx_device / _xx2k_device /
+  _k2y_device / _y2k_device / _k2xx_device / _xx2x_device / _solve_device
+      take and return device arrays (here: torch CUDA complex64 tensors instead of reikna arrays)
+  to_device, to_host, release
+  set_sense, reset_sense, s2x, x2s, forward_one2many, adjoint_many2one, selfadjoint_one2many2one
+
+There is no CPU processor: `NUFFT()` without a CUDA device raises.
+"""
+import ctypes
+
+import numpy
+import torch
+
+from . import _lib, planmath
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _as_device(device_indx):
+    """Accept torch.device, 'cuda:N', int, or a reference-style helper.device_list() tuple."""
+    if device_indx is None:
+        raise RuntimeError('pynufft_b200.NUFFT has no CPU processor: pass a CUDA device, e.g. NUFFT("cuda:0")')
+    if isinstance(device_indx, torch.device):
+        dev = device_indx
+    elif isinstance(device_indx, int):
+        dev = torch.device('cuda', device_indx)
+    elif isinstance(device_indx, str):
+        dev = torch.device(device_indx)
+    elif isinstance(device_indx, (tuple, list)) and len(device_indx) >= 3:
+        dev = torch.device('cuda', int(device_indx[2]))      # ('cuda', api_n, dev_num, ...) helper.py:1195
+    else:
+        raise TypeError('device must be a torch.device, "cuda:N" or an int')
+    if dev.type != 'cuda':
+        raise RuntimeError('pynufft_b200 runs on CUDA devices only (got %s)' % dev)
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    return dev
+
+
+class NUFFT:
+    def __init__(self, device_indx=None, legacy=None):
+        if legacy:
+            raise NotImplementedError('the legacy CSR device format is out of scope (SURVEY.md 8f)')
+        self.device = _as_device(device_indx)
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('no CUDA device available; pynufft_b200 has no CPU fallback')
+        self.dtype = numpy.complex64
+        self.processor = 'hsa'
+        self.verbosity = 0
+        self._plan = None
+        self.Nd = self.Kd = self.Jd = ()
+        self.ndims = 0
+        self.ft_axes = ()
+        self.batch = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plan / release
+    def plan(self, om, Nd, Kd, Jd, ft_axes=None, batch=None, radix=None):
+        # argument errors exactly as helper.plan (src/_helper/helper.py:644-654)
+        if type(Nd) != tuple:
+            raise TypeError('Nd must be tuple, e.g. (256, 256)')
+        if type(Kd) != tuple:
+            raise TypeError('Kd must be tuple, e.g. (512, 512)')
+        if type(Jd) != tuple:
+            raise TypeError('Jd must be tuple, e.g. (6, 6)')
+        if (len(Nd) != len(Kd)) or (len(Nd) != len(Jd)):
+            raise KeyError('Nd, Kd, Jd must be in the same length, e.g. Nd=(256,256),Kd=(512,512),Jd=(6,6)')
+        nd = len(Nd)
+        if ft_axes is not None and tuple(ft_axes) != tuple(range(nd)):
+            raise NotImplementedError('partial ft_axes is unsupported (broken upstream, SURVEY.md 8c)')
+        if radix not in (None, 1):
+            raise NotImplementedError('radix > 1 is out of scope (SURVEY.md 8f)')
+        if nd > _lib.MAX_DIM:
+            raise NotImplementedError('ndim <= 3 supported')
+        self.release()
+        om = numpy.ascontiguousarray(numpy.asarray(om, dtype=numpy.float64))   # float32 om is up-cast (documented)
+        if om.ndim == 1:
+            om = om.reshape(-1, 1)
+        if om.ndim != 2 or om.shape[1] != nd:
+            raise ValueError('om must have shape (M, %d)' % nd)
+        M = om.shape[0]
+
+        alpha = numpy.zeros((nd, _lib.MAX_L), dtype=numpy.float64)
+        alpha_len = numpy.zeros(nd, dtype=numpy.int32)
+        Tm = numpy.zeros((nd, _lib.MAX_J * _lib.MAX_J), dtype=numpy.float64)
+        sn_parts, self.st = [], {}
+        self.st['alpha'], self.st['beta'] = [], []
+        for d in range(nd):
+            a, b = planmath.kb_fit_alpha(Nd[d], Jd[d], Kd[d])
+            alpha[d, :len(a)] = a
+            alpha_len[d] = len(a)
+            Tm[d, :Jd[d] * Jd[d]] = planmath.interp_T(Nd[d], Jd[d], Kd[d], a, b).reshape(-1)
+            sn_parts.append(numpy.real(planmath.scaling_vector(Nd[d], Kd[d], a, b)))
+            self.st['alpha'].append(a)
+            self.st['beta'].append(b)
+        tensor_sn = numpy.ascontiguousarray(numpy.concatenate(sn_parts).astype(numpy.float32))
+
+        Nd_a = numpy.asarray(Nd, dtype=numpy.int32)
+        Kd_a = numpy.asarray(Kd, dtype=numpy.int32)
+        Jd_a = numpy.asarray(Jd, dtype=numpy.int32)
+        handle = _vp()
+        with torch.cuda.device(self.device):
+            rc = self._lib.b200nufft_plan_create(
+                ctypes.byref(handle), self.device.index, nd, Nd_a.ctypes.data, Kd_a.ctypes.data, Jd_a.ctypes.data,
+                M, om.ctypes.data, 1 if batch is None else int(batch), alpha.ctypes.data, alpha_len.ctypes.data,
+                Tm.ctypes.data, tensor_sn.ctypes.data, _stream())
+        _lib.check(rc)
+        self._plan = handle
+
+        self.ndims = nd
+        self.ft_axes = tuple(range(nd))
+        self.Nd, self.Kd, self.Jd = Nd, Kd, Jd
+        self.st.update(dict(Nd=Nd, Kd=Kd, Jd=Jd, M=numpy.int32(M), om=om, tol=0, tensor_sn=tensor_sn))
+        self.parallel_flag = 0 if batch is None else 1
+        self.batch = 1 if batch is None else int(batch)
+        self.M = int(M)
+        self.Ndprod = int(numpy.prod(Nd))
+        self.Kdprod = int(numpy.prod(Kd))
+        self.Jdprod = int(numpy.prod(Jd))
+        if self.parallel_flag == 0:
+            self.multi_Nd, self.multi_Kd, self.multi_M = Nd, Kd, (M,)
+        else:
+            self.multi_Nd, self.multi_Kd, self.multi_M = Nd + (self.batch,), Kd + (self.batch,), (M, self.batch)
+        self._sense = None
+        return 0
+
+    def release(self):
+        if getattr(self, '_plan', None) is not None:
+            self._lib.b200nufft_plan_destroy(self._plan)
+            self._plan = None
+        self._sense = None
+
+    # ------------------------------------------------------------------ helpers
+    def _require_plan(self):
+        if self._plan is None:
+            raise RuntimeError('plan() has not been called')
+
+    def _nb_of(self, t, base_ndim, what):
+        """Coil count of a device array whose single-coil rank is base_ndim (batch axis is last)."""
+        if t.dim() == base_ndim:
+            return 1
+        if t.dim() == base_ndim + 1:
+            return int(t.shape[-1])
+        raise ValueError('%s has wrong rank %d' % (what, t.dim()))
+
+    def _check_dev(self, t, shape_prefix, what):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.complex64):
+            raise TypeError('%s must be a CUDA complex64 torch tensor (use to_device())' % what)
+        if tuple(t.shape[:len(shape_prefix)]) != tuple(shape_prefix):
+            raise ValueError('%s has shape %s, expected %s(+batch)' % (what, tuple(t.shape), tuple(shape_prefix)))
+        return t.contiguous()
+
+    def _new_grid(self, nb, batched):
+        """Kd(+ (B,)) view of coil-major storage (B, *Kd)."""
+        store = torch.empty((nb,) + tuple(self.Kd), dtype=torch.complex64, device=self.device)
+        if not batched:
+            return store[0], store
+        return store.permute(*range(1, self.ndims + 1), 0), store
+
+    def _grid_storage(self, k, what='k'):
+        """Return (coil-major contiguous storage tensor, nb, batched) for a user grid tensor."""
+        if not (isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.complex64):
+            raise TypeError('%s must be a CUDA complex64 torch tensor' % what)
+        if tuple(k.shape[:self.ndims]) != tuple(self.Kd):
+            raise ValueError('%s has shape %s, expected %s(+batch)' % (what, tuple(k.shape), tuple(self.Kd)))
+        nb = self._nb_of(k, self.ndims, what)
+        if k.dim() == self.ndims:
+            return k.contiguous(), 1, False
+        cm = k.permute(self.ndims, *range(self.ndims))
+        return cm.contiguous(), nb, True         # no copy when k is already a coil-major view
+
+    # ------------------------------------------------------------------ host <-> device
+    def to_device(self, x, shape=None):
+        return torch.from_numpy(numpy.ascontiguousarray(numpy.asarray(x).astype(self.dtype))).to(self.device)
+
+    def to_host(self, data):
+        return data.detach().cpu().numpy()
+
+    # ------------------------------------------------------------------ device stages
+    def _x2xx_device(self, x):
+        self._require_plan()
+        x = self._check_dev(x, self.Nd, 'x')
+        out = torch.empty_like(x)
+        _lib.check(self._lib.b200nufft_x2xx(self._plan, _ptr(x), _ptr(out), self._nb_of(x, self.ndims, 'x'), 0,
+                                            _stream()))
+        return out
+
+    def _xx2x_device(self, xx):
+        return self._x2xx_device(xx)
+
+    def _xx2k_device(self, xx):
+        self._require_plan()
+        xx = self._check_dev(xx, self.Nd, 'xx')
+        nb = self._nb_of(xx, self.ndims, 'xx')
+        view, store = self._new_grid(nb, xx.dim() == self.ndims + 1)
+        _lib.check(self._lib.b200nufft_scale_pad(self._plan, _ptr(xx), _ptr(store), nb, 0, 0, None, _stream()))
+        _lib.check(self._lib.b200nufft_fft(self._plan, _ptr(store), nb, 0, _stream()))
+        return view
+
+    def _k2y_device(self, k):
+        self._require_plan()
+        store, nb, batched = self._grid_storage(k)
+        y = torch.empty((self.M, nb) if batched else (self.M,), dtype=torch.complex64, device=self.device)
+        _lib.check(self._lib.b200nufft_interp(self._plan, _ptr(store), _ptr(y), nb, _stream()))
+        return y
+
+    def _y2k_device(self, y):
+        self._require_plan()
+        y = self._check_dev(y, (self.M,), 'y')
+        nb = self._nb_of(y, 1, 'y')
+        view, store = self._new_grid(nb, y.dim() == 2)
+        _lib.check(self._lib.b200nufft_gridding(self._plan, _ptr(y), _ptr(store), nb, _stream()))
+        return view
+
+    def _k2xx_device(self, k):
+        """Inverse FFT (in place on k when k is a coil-major view, like the reference's in-place FFT) + crop."""
+        self._require_plan()
+        store, nb, batched = self._grid_storage(k)
+        xx = torch.empty(tuple(self.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=self.device)
+        _lib.check(self._lib.b200nufft_fft(self._plan, _ptr(store), nb, 1, _stream()))
+        _lib.check(self._lib.b200nufft_crop_scale(self._plan, _ptr(store), _ptr(xx), nb, 0, 0, None, _stream()))
+        return xx
+
+    def _forward_device(self, gx):
+        self._require_plan()
+        gx = self._check_dev(gx, self.Nd, 'x')
+        nb = self._nb_of(gx, self.ndims, 'x')
+        y = torch.empty((self.M, nb) if gx.dim() == self.ndims + 1 else (self.M,), dtype=torch.complex64,
+                        device=self.device)
+        _lib.check(self._lib.b200nufft_forward(self._plan, _ptr(gx), _ptr(y), nb, _stream()))
+        return y
+
+    def _adjoint_device(self, gy):
+        self._require_plan()
+        gy = self._check_dev(gy, (self.M,), 'y')
+        nb = self._nb_of(gy, 1, 'y')
+        x = torch.empty(tuple(self.Nd) + ((nb,) if gy.dim() == 2 else ()), dtype=torch.complex64, device=self.device)
+        _lib.check(self._lib.b200nufft_adjoint(self._plan, _ptr(gy), _ptr(x), nb, _stream()))
+        return x
+
+    def _selfadjoint_device(self, gx):
+        return self._adjoint_device(self._forward_device(gx))
+
+    def _solve_device(self, gy, solver=None, *args, **kwargs):
+        from .solve import solve
+        return solve(self, gy, solver, *args, **kwargs)
+
+    # ------------------------------------------------------------------ multi-coil (NUFFT_hsa API)
+    def set_sense(self, coil_profile):
+        self._require_plan()
+        shape = tuple(coil_profile.shape)
+        if shape != tuple(self.Nd) + (self.batch,):
+            print('The shape of coil_profile is ', shape)
+            print('But it should be', tuple(self.Nd) + (self.batch,))
+            raise ValueError
+        if isinstance(coil_profile, torch.Tensor):
+            self._sense = coil_profile.to(self.device, torch.complex64).contiguous()
+        else:
+            self._sense = self.to_device(coil_profile)
+
+    def reset_sense(self):
+        self._sense = None        # == all ones (linalg/nufft_hsa.py:333-335)
+
+    def s2x(self, s):
+        self._require_plan()
+        s = self._check_dev(s, self.Nd, 's')
+        x = s.unsqueeze(-1).expand(*s.shape, self.batch)
+        if self._sense is not None:
+            return x * self._sense
+        return x.contiguous()
+
+    def x2s(self, x):
+        self._require_plan()
+        x = self._check_dev(x, tuple(self.Nd) + (self.batch,), 'x')
+        if self._sense is not None:
+            x = x * self._sense.conj()
+        return x.mean(dim=-1)
+
+    def forward_one2many(self, s):
+        self._require_plan()
+        host = not isinstance(s, torch.Tensor)
+        gs = self.to_device(s) if host else s
+        gs = self._check_dev(gs, self.Nd, 's')
+        if gs.dim() != self.ndims:
+            raise ValueError('s must have shape Nd')
+        y = torch.empty((self.M, self.batch), dtype=torch.complex64, device=self.device)
+        sens = _ptr(self._sense) if self._sense is not None else None
+        _lib.check(self._lib.b200nufft_forward_one2many(self._plan, _ptr(gs), sens, _ptr(y), self.batch, _stream()))
+        return self.to_host(y) if host else y
+
+    def adjoint_many2one(self, y):
+        self._require_plan()
+        host = not isinstance(y, torch.Tensor)
+        gy = self.to_device(y) if host else y
+        gy = self._check_dev(gy, (self.M, self.batch), 'y')
+        s = torch.empty(tuple(self.Nd), dtype=torch.complex64, device=self.device)
+        sens = _ptr(self._sense) if self._sense is not None else None
+        _lib.check(self._lib.b200nufft_adjoint_many2one(self._plan, _ptr(gy), sens, _ptr(s), self.batch, _stream()))
+        return self.to_host(s) if host else s
+
+    def selfadjoint_one2many2one(self, s):
+        host = not isinstance(s, torch.Tensor)
+        gs = self.to_device(s) if host else s
+        out = self.adjoint_many2one(self.forward_one2many(gs))
+        return self.to_host(out) if host else out
+
+    # ------------------------------------------------------------------ host API (numpy in / out)
+    def _host_c64(self, a, shape_prefix, what):
+        a = numpy.ascontiguousarray(numpy.asarray(a).astype(self.dtype))
+        if tuple(a.shape[:len(shape_prefix)]) != tuple(shape_prefix) or a.ndim > len(shape_prefix) + 1:
+            raise ValueError('%s has shape %s, expected %s(+batch)' % (what, a.shape, tuple(shape_prefix)))
+        return a
+
+    def forward(self, x):
+        self._require_plan()
+        x = self._host_c64(x, self.Nd, 'x')
+        nb = x.shape[-1] if x.ndim == self.ndims + 1 else 1
+        y = numpy.empty((self.M, nb) if x.ndim == self.ndims + 1 else (self.M,), dtype=self.dtype)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200nufft_forward_host(self._plan, x.ctypes.data, y.ctypes.data, nb, _stream()))
+        return y
+
+    def adjoint(self, y):
+        self._require_plan()
+        y = self._host_c64(y, (self.M,), 'y')
+        nb = y.shape[-1] if y.ndim == 2 else 1
+        x = numpy.empty(tuple(self.Nd) + ((nb,) if y.ndim == 2 else ()), dtype=self.dtype)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200nufft_adjoint_host(self._plan, y.ctypes.data, x.ctypes.data, nb, _stream()))
+        return x
+
+    def selfadjoint(self, x):
+        return self.to_host(self._selfadjoint_device(self.to_device(x)))
+
+    def solve(self, y, *args, **kwargs):
+        return self.to_host(self._solve_device(self.to_device(y), *args, **kwargs))
+
+    def x2xx(self, x):
+        return self.to_host(self._x2xx_device(self.to_device(x)))
+
+    def xx2x(self, xx):
+        return self.to_host(self._xx2x_device(self.to_device(xx)))
+
+    def xx2k(self, xx):
+        return self.to_host(self._xx2k_device(self.to_device(xx)))
+
+    def k2xx(self, k):
+        return self.to_host(self._k2xx_device(self.to_device(k)))
+
+    def k2y(self, k):
+        return self.to_host(self._k2y_device(self.to_device(k)))
+
+    def y2k(self, y):
+        return self.to_host(self._y2k_device(self.to_device(y)))
+
+    # ------------------------------------------------------------------ parity / introspection
+    def _plan_arrays(self):
+        """(kindx uint32 (M,sumJ), udata c64 (M,sumJ), k0 int32 (M,d), perm int32 (M,), tile, sub) as numpy."""
+        self._require_plan()
+        sumJ = int(numpy.sum(self.Jd))
+        dev = self.device
+        kindx = torch.empty((self.M, sumJ), dtype=torch.int32, device=dev)
+        udata = torch.empty((self.M, sumJ), dtype=torch.complex64, device=dev)
+        k0 = torch.empty((self.M, self.ndims), dtype=torch.int32, device=dev)
+        perm = torch.empty((self.M,), dtype=torch.int32, device=dev)
+        tile = numpy.zeros(2 * self.ndims, dtype=numpy.int32)
+        _lib.check(self._lib.b200nufft_plan_get_kindx(self._plan, _ptr(kindx), _stream()))
+        _lib.check(self._lib.b200nufft_plan_get_udata(self._plan, _ptr(udata), _stream()))
+        _lib.check(self._lib.b200nufft_plan_get_k0(self._plan, _ptr(k0), _stream()))
+        _lib.check(self._lib.b200nufft_plan_get_perm(self._plan, _ptr(perm), _stream()))
+        _lib.check(self._lib.b200nufft_plan_get_tile(self._plan, tile.ctypes.data))
+        return (kindx.cpu().numpy().view(numpy.uint32), udata.cpu().numpy(), k0.cpu().numpy(), perm.cpu().numpy(),
+                tuple(int(v) for v in tile[:self.ndims]), tuple(int(v) for v in tile[self.ndims:]))
+
+    def set_variant(self, interp=0, gridding=0):
+        """0 auto, 1 generic kernels, 2 tiled kernels (error if the geometry is unsupported)."""
+        self._require_plan()
+        _lib.check(self._lib.b200nufft_set_variant(self._plan, int(interp), int(gridding)))

@@ -1,0 +1,166 @@
+"""
+Device solvers on the NUFFT class: 'cg' and 'L1TVOLS' (+ 'dc'), the algorithms of
+linalg/solve_device.py (cg :351-481, L1TVOLS :74-275; batched cg linalg/solve_hsa.py:551-682).
+
+Same iterates as the reference, different execution: each CG iteration is
+interp + gridding + 3 fused streaming kernels, and alpha/beta/rho live in a small device buffer
+(float64 pairs) instead of being fetched with .get() three times per iteration
+(solve_device.py:424,432,449).  When a process group is passed (coil-sharded operators,
+pynufft_b200/dist.py) the two scalars are summed with one all-reduce each.
+"""
+import ctypes
+
+import numpy
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t):
+    return _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _flat(view):
+    """Underlying contiguous storage of a grid view returned by _y2k_device/_new_grid."""
+    if view.is_contiguous():
+        return view
+    nd = view.dim() - 1
+    cm = view.permute(nd, *range(nd))
+    assert cm.is_contiguous()
+    return cm
+
+
+def cg(nufft, gy, maxiter=30, group=None):
+    """k-space CG on G = interp^H interp, x0 = b, exactly `maxiter` steps, then k2xx and /sn."""
+    L = nufft._lib
+    st = _stream
+    allreduce = None
+    if group is not None:
+        import torch.distributed as dist
+        allreduce = lambda t: dist.all_reduce(t, group=group)
+
+    def G(view):
+        return nufft._y2k_device(nufft._k2y_device(view))
+
+    b = nufft._y2k_device(gy)
+    x = b.clone(memory_format=torch.preserve_format)
+    Ax = G(x)
+    r = torch.empty_like(_flat(b))
+    p_store = torch.empty_like(_flat(b))
+    n = r.numel()
+    # scalars: [rsold(2), pAp(2), rsnew(2)] float64
+    sc = torch.zeros(6, dtype=torch.float64, device=nufft.device)
+    rsold, pAp, rsnew = sc[0:2], sc[2:4], sc[4:6]
+    _lib.check(L.b200nufft_cg_init(_ptr(_flat(b)), _ptr(_flat(Ax)), _ptr(r), _ptr(p_store), _ptr(rsold), n, st()))
+    if allreduce:
+        allreduce(rsold)
+    del Ax
+    xs = _flat(x)
+    # p as a grid view with the same layout as b so that it can be fed to _k2y_device without a copy
+    if b.is_contiguous():
+        p_view = p_store
+    else:
+        nd = b.dim() - 1
+        p_view = p_store.permute(*range(1, nd + 1), 0)
+    for _ in range(maxiter):
+        Ap = G(p_view)
+        pAp.zero_()
+        _lib.check(L.b200nufft_dotc(_ptr(p_store), _ptr(_flat(Ap)), n, _ptr(pAp), st()))
+        if allreduce:
+            allreduce(pAp)
+        rsnew.zero_()
+        _lib.check(L.b200nufft_cg_update_xr(_ptr(xs), _ptr(r), _ptr(p_store), _ptr(_flat(Ap)), _ptr(rsold),
+                                            _ptr(pAp), _ptr(rsnew), n, st()))
+        if allreduce:
+            allreduce(rsnew)
+        _lib.check(L.b200nufft_cg_update_p(_ptr(p_store), _ptr(r), _ptr(rsnew), _ptr(rsold), n, st()))
+        rsold.copy_(rsnew)
+        del Ap
+    # inverse FFT, crop, divide by sn  (solve_device.py:463-480)
+    nb = 1 if x.dim() == nufft.ndims else int(x.shape[-1])
+    x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if x.dim() == nufft.ndims + 1 else ()), dtype=torch.complex64,
+                     device=nufft.device)
+    _lib.check(L.b200nufft_fft(nufft._plan, _ptr(xs), nb, 1, st()))
+    _lib.check(L.b200nufft_crop_scale(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, st()))
+    return x2
+
+
+def _sampling_density(nufft):
+    """|y2k(1)|  (solve_device.py:25-36)"""
+    ones = torch.ones((nufft.M,), dtype=torch.complex64, device=nufft.device)
+    return nufft._y2k_device(ones).abs()
+
+
+def _laplacian_kernel(nufft):
+    """FFT of the (2d+1)-point Laplacian stencil on the Kd grid (src/_helper/helper.py:11-45)."""
+    nd = nufft.ndims
+    uker = numpy.zeros(nufft.Kd, dtype=numpy.complex64)
+    uker[(0,) * nd] = -2.0 * nd
+    for pp in range(nd):
+        i1 = [0] * nd
+        i1[pp] = 1
+        uker[tuple(i1)] = 1
+        i1[pp] = -1
+        uker[tuple(i1)] = 1
+    return numpy.fft.fftn(uker)
+
+
+def L1TVOLS(nufft, gy, maxiter, rho):
+    """Split-Bregman total variation, device variant (solve_device.py:74-275)."""
+    if nufft.batch != 1 or gy.dim() != 1:
+        raise ValueError('L1TVOLS is single-coil (as in the reference)')
+    L = nufft._lib
+    st = _stream
+    mu = 1.0
+    LMBD = rho * mu
+    nd = nufft.ndims
+    dev = nufft.device
+    uker = (mu * _sampling_density(nufft).cpu().numpy() - LMBD * _laplacian_kernel(nufft)).astype(numpy.complex64)
+    uker = torch.from_numpy(uker).to(dev)
+    AHy = nufft._adjoint_device(gy)
+    Nd = tuple(nufft.Nd)
+    n = int(numpy.prod(Nd))
+    xkp1 = torch.zeros(Nd, dtype=torch.complex64, device=dev)
+    AHyk = torch.zeros(Nd, dtype=torch.complex64, device=dev)
+    dd = torch.zeros((nd,) + Nd, dtype=torch.complex64, device=dev)
+    bb = torch.zeros((nd,) + Nd, dtype=torch.complex64, device=dev)
+    rhs = torch.empty(Nd, dtype=torch.complex64, device=dev)
+    k = torch.empty(tuple(nufft.Kd), dtype=torch.complex64, device=dev)
+    for _ in range(int(maxiter)):
+        _lib.check(L.b200nufft_tv_rhs(nufft._plan, _ptr(AHyk), _ptr(dd), _ptr(bb), mu, LMBD, _ptr(rhs), st()))
+        # xkp1 = k2xx(xx2k(rhs) / uker): zero-pad + FFT without sn scaling (:174-181)
+        _lib.check(L.b200nufft_scale_pad(nufft._plan, _ptr(rhs), _ptr(k), 1, 0, 0, None, st()))
+        _lib.check(L.b200nufft_fft(nufft._plan, _ptr(k), 1, 0, st()))
+        _lib.check(L.b200nufft_cdiv(_ptr(k), _ptr(uker), k.numel(), st()))
+        _lib.check(L.b200nufft_fft(nufft._plan, _ptr(k), 1, 1, st()))
+        _lib.check(L.b200nufft_crop_scale(nufft._plan, _ptr(k), _ptr(xkp1), 1, 0, 0, None, st()))
+        zf = nufft._selfadjoint_device(xkp1)
+        _lib.check(L.b200nufft_tv_shrink(nufft._plan, _ptr(xkp1), _ptr(dd), _ptr(bb), LMBD, st()))
+        _lib.check(L.b200nufft_tv_bregman(_ptr(AHyk), _ptr(zf), _ptr(AHy), n, st()))
+    return xkp1
+
+
+def density_compensation(nufft, gy, maxiter=1):
+    """'dc': Pipe's iteration W <- W / (A A^H W), then adjoint(W*y)  (solve_device.py:277-310, solve_cpu.py:165-225)."""
+    W = torch.ones((nufft.M,), dtype=torch.complex64, device=nufft.device)
+    for _ in range(int(maxiter)):
+        E = nufft._forward_device(nufft._adjoint_device(W))
+        W = W / E
+    return nufft._adjoint_device(W * gy)
+
+
+def solve(nufft, gy, solver=None, maxiter=30, *args, **kwargs):
+    """solve(nufft, y, solver, maxiter, **kw) -- linalg/solve_device.py:312."""
+    if solver == 'cg':
+        return cg(nufft, gy, maxiter=maxiter, **kwargs)
+    if solver == 'L1TVOLS':
+        return L1TVOLS(nufft, gy, maxiter=maxiter, *args, **kwargs)
+    if solver == 'dc':
+        return density_compensation(nufft, gy, maxiter=maxiter)
+    raise ValueError("solver must be 'cg', 'L1TVOLS' or 'dc' (got %r)" % (solver,))

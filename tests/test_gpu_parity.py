@@ -1,0 +1,299 @@
+"""
+GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libb200nufft.so) via pynufft_b200.NUFFT; the checker is the oracle and the committed golden
+vectors of the unmodified reference.
+
+Tolerances: indices / k0 / sort permutation bit-exact; complex64 values 1e-5 relative L2
+(the reference's own CPU-vs-device band is 1e-7..4e-6).
+"""
+import numpy
+import pytest
+import torch
+
+from oracle import nufft_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    a = numpy.asarray(a).ravel()
+    b = numpy.asarray(b).ravel()
+    return numpy.linalg.norm(a - b) / numpy.linalg.norm(b)
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda', 0)
+
+
+def make(dev, om, Nd, Kd, Jd, batch=None):
+    import pynufft_b200
+    A = pynufft_b200.NUFFT(dev)
+    assert A.plan(om, Nd, Kd, Jd, batch=batch) == 0
+    return A
+
+
+VARIANTS = [1, 0]   # generic kernels, auto (tiled where supported)
+
+
+# ------------------------------------------------------------------------------ plan
+def test_plan_matches_reference(golden, dev):
+    A = make(dev, golden['om'], golden['Nd'], golden['Kd'], golden['Jd'])
+    kindx, udata, k0, perm, tile, sub = A._plan_arrays()
+    assert numpy.array_equal(kindx, golden['kindx'])                      # bit-exact indices
+    assert numpy.max(numpy.abs(udata - golden['udata'])) < 2e-6
+    assert rel(udata, golden['udata']) < 1e-6
+    p = orc.Plan(golden['om'], golden['Nd'], golden['Kd'], golden['Jd'])
+    assert numpy.array_equal(k0, p.k0)
+    assert (tile, sub) == orc.default_tiles(golden['Kd'])
+    assert numpy.array_equal(perm, orc.sort_permutation(p.k0, golden['Kd'], tile, sub))   # bit-exact permutation
+
+
+# ------------------------------------------------------------------------------ operator vs golden
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_operator_matches_reference(golden, dev, variant):
+    A = make(dev, golden['om'], golden['Nd'], golden['Kd'], golden['Jd'])
+    A.set_variant(variant, variant)
+    x, y = golden['x'], golden['y_in']
+    assert rel(A.x2xx(x), golden['xx']) < TOL
+    assert rel(A.xx2k(golden['xx']), golden['k']) < TOL
+    assert rel(A.k2y(golden['k']), golden['forward']) < TOL
+    assert rel(A.y2k(y), golden['y2k']) < TOL
+    assert rel(A.forward(x), golden['forward']) < TOL
+    assert rel(A.adjoint(y), golden['adjoint']) < TOL
+    assert rel(A.selfadjoint(x), golden['selfadjoint']) < TOL
+    # device-array entry points (tests/test_init_device.py:70-72 of the reference call these)
+    gx = A.to_device(x)
+    gy = A._forward_device(gx)
+    assert rel(A.to_host(gy), golden['forward']) < TOL
+    assert rel(A.to_host(A._adjoint_device(A.to_device(y))), golden['adjoint']) < TOL
+    k = A._xx2k_device(A._x2xx_device(gx))
+    assert rel(A.to_host(A._xx2x_device(A._k2xx_device(A._y2k_device(A._k2y_device(k))))), golden['selfadjoint']) < TOL
+    A.release()
+
+
+def test_solvers_match_reference_device_algorithms(golden, dev):
+    if 'cg10' not in golden:
+        pytest.skip('no solver vectors for this case')
+    A = make(dev, golden['om'], golden['Nd'], golden['Kd'], golden['Jd'])
+    y = golden['solve_y']
+    assert rel(A.solve(y, 'cg', maxiter=10), golden['cg10']) < 1e-4
+    assert rel(A.solve(y, 'L1TVOLS', maxiter=5, rho=2), golden['l1tvols5']) < 1e-4
+
+
+# ------------------------------------------------------------------------------ edge cases
+def test_argument_errors(dev):
+    import pynufft_b200
+    A = pynufft_b200.NUFFT(dev)
+    om = numpy.zeros((4, 2))
+    with pytest.raises(TypeError):
+        A.plan(om, [8, 8], (16, 16), (4, 4))
+    with pytest.raises(KeyError):
+        A.plan(om, (8, 8), (16, 16), (4,))
+    with pytest.raises(RuntimeError):
+        A.forward(numpy.zeros((8, 8)))
+    A.plan(om, (8, 8), (16, 16), (4, 4))
+    with pytest.raises(ValueError):
+        A.forward(numpy.zeros((8, 9)))
+    with pytest.raises(ValueError):
+        A.solve(numpy.zeros(4), 'nope')
+
+
+def test_empty_and_single_sample(dev):
+    A = make(dev, numpy.zeros((0, 2)), (8, 8), (16, 16), (4, 4))
+    assert A.forward(numpy.ones((8, 8))).shape == (0,)
+    assert numpy.all(A.adjoint(numpy.zeros((0,))) == 0)
+    om = numpy.array([[0.3, -1.2]])
+    A = make(dev, om, (8, 8), (16, 16), (4, 4))
+    O = orc.NUFFT()
+    O.plan(om, (8, 8), (16, 16), (4, 4))
+    x = (numpy.arange(64).reshape(8, 8) + 1j).astype(numpy.complex64)
+    assert rel(A.forward(x), O.forward(x)) < TOL
+    assert rel(A.adjoint(numpy.array([1 - 2j])), O.adjoint(numpy.array([1 - 2j]))) < TOL
+
+
+def test_samples_on_edges_and_duplicates(dev):
+    # +-pi (wrap), exact grid points, many duplicates (collisions in the scatter)
+    K = 32
+    base = numpy.array([[-numpy.pi, numpy.pi, 0.0], [numpy.pi, -numpy.pi, numpy.pi], [0, 0, 0],
+                        [2 * numpy.pi / K * 5, -2 * numpy.pi / K * 7, 2 * numpy.pi / K * 15.5]])
+    om = numpy.concatenate([base, numpy.repeat(base[3:4], 300, axis=0)])
+    Nd, Kd, Jd = (16, 16, 16), (K, K, K), (6, 6, 6)
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, Jd)
+    rng = numpy.random.default_rng(0)
+    x = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    y = (rng.standard_normal(om.shape[0]) + 1j * rng.standard_normal(om.shape[0])).astype(numpy.complex64)
+    for v in VARIANTS:
+        A = make(dev, om, Nd, Kd, Jd)
+        A.set_variant(v, v)
+        kindx, _, _, _, _, _ = A._plan_arrays()
+        assert numpy.array_equal(kindx, O.p.kindx)
+        assert rel(A.forward(x), O.forward(x)) < TOL
+        assert rel(A.adjoint(y), O.adjoint(y)) < TOL
+
+
+@pytest.mark.parametrize('geom', [
+    ((20, 18, 22), (40, 36, 44), (6, 6, 6)),     # K not a multiple of the tile: ragged last tile
+    ((10, 12, 8), (24, 20, 16), (6, 6, 6)),      # tile box wraps onto itself (K < tile + J - 1)
+    ((16, 16, 16), (48, 32, 40), (6, 6, 6)),     # K/N != 2 in some dims
+    ((12, 12, 12), (24, 24, 24), (5, 4, 3)),     # mixed J (generic kernels)
+    ((30,), (60,), (7,)),
+    ((33, 20), (66, 50), (6, 3)),
+])
+def test_ragged_geometries(dev, geom):
+    Nd, Kd, Jd = geom
+    rng = numpy.random.default_rng(5)
+    om = rng.uniform(-numpy.pi, numpy.pi, (3000, len(Nd)))
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, Jd)
+    x = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    y = (rng.standard_normal(3000) + 1j * rng.standard_normal(3000)).astype(numpy.complex64)
+    for v in VARIANTS:
+        A = make(dev, om, Nd, Kd, Jd)
+        A.set_variant(v, v)
+        kindx, _, k0, perm, tile, sub = A._plan_arrays()
+        assert numpy.array_equal(kindx, O.p.kindx)
+        assert numpy.array_equal(perm, orc.sort_permutation(O.p.k0, Kd, tile, sub))
+        assert rel(A.forward(x), O.forward(x)) < TOL
+        assert rel(A.adjoint(y), O.adjoint(y)) < TOL
+
+
+# ------------------------------------------------------------------------------ config 1 (2D 256^2, PROPELLER)
+def propeller(nblades=20, nlines=24, npts=256):
+    """Synthetic PROPELLER trajectory with the structure of the reference's om2D.npz."""
+    kx = (numpy.arange(npts) - npts / 2) * (2 * numpy.pi / npts)
+    ky = (numpy.arange(nlines) - nlines / 2) * (2 * numpy.pi / npts)
+    gx, gy = numpy.meshgrid(kx, ky, indexing='xy')
+    out = []
+    for b in range(nblades):
+        th = numpy.deg2rad(9.0 * b)
+        out.append(numpy.stack([gx * numpy.cos(th) - gy * numpy.sin(th), gx * numpy.sin(th) + gy * numpy.cos(th)], -1).reshape(-1, 2))
+    return numpy.clip(numpy.concatenate(out), -numpy.pi, numpy.pi)
+
+
+def test_config1_2d_256(dev):
+    om = propeller()
+    Nd, Kd, Jd = (256, 256), (512, 512), (6, 6)
+    rng = numpy.random.default_rng(11)
+    x = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, Jd)
+    A = make(dev, om, Nd, Kd, Jd)
+    kindx, udata, _, perm, tile, sub = A._plan_arrays()
+    assert numpy.array_equal(kindx, O.p.kindx)
+    assert rel(udata, O.p.udata) < 1e-6
+    assert numpy.array_equal(perm, orc.sort_permutation(O.p.k0, Kd, tile, sub))
+    y = O.forward(x)
+    assert rel(A.forward(x), y) < TOL
+    assert rel(A.adjoint(y.astype(numpy.complex64)), O.adjoint(y.astype(numpy.complex64))) < TOL
+
+
+# ------------------------------------------------------------------------------ config 2 (multi-coil)
+def coil_maps(Nd, B, seed=0):
+    rng = numpy.random.default_rng(seed)
+    grids = numpy.meshgrid(*[numpy.arange(n) for n in Nd], indexing='ij')
+    maps = numpy.zeros(Nd + (B,), dtype=numpy.complex64)
+    for c in range(B):
+        ang = 2 * numpy.pi * c / B
+        ctr = [Nd[0] / 2 + 0.45 * Nd[0] * numpy.cos(ang), Nd[1] / 2 + 0.45 * Nd[1] * numpy.sin(ang)] + \
+              [n / 2 for n in Nd[2:]]
+        r2 = sum((g - c0) ** 2 for g, c0 in zip(grids, ctr))
+        maps[..., c] = numpy.exp(-r2 / (2 * (0.6 * Nd[0]) ** 2)) * numpy.exp(1j * rng.uniform(0, 2 * numpy.pi))
+    return maps
+
+
+@pytest.mark.parametrize('geom', [((64, 64), (128, 128), (6, 6), 8), ((16, 16, 16), (32, 32, 32), (6, 6, 6), 3)])
+def test_multicoil(dev, geom):
+    Nd, Kd, Jd, B = geom
+    rng = numpy.random.default_rng(3)
+    om = rng.uniform(-numpy.pi, numpy.pi, (2500, len(Nd)))
+    sens = coil_maps(Nd, B)
+    s = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    xb = (rng.standard_normal(Nd + (B,)) + 1j * rng.standard_normal(Nd + (B,))).astype(numpy.complex64)
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, Jd, batch=B)
+    A = make(dev, om, Nd, Kd, Jd, batch=B)
+    # batched forward/adjoint (Nd+(B,) <-> (M,B)), batch innermost
+    yb = O.forward(xb)
+    assert rel(A.forward(xb), yb) < TOL
+    assert rel(A.adjoint(yb.astype(numpy.complex64)), O.adjoint(yb.astype(numpy.complex64))) < TOL
+    # default sense == ones
+    assert rel(A.forward_one2many(s), O.forward_one2many(s)) < TOL
+    with pytest.raises(ValueError):
+        A.set_sense(sens[..., :-1])
+    A.set_sense(sens)
+    O.set_sense(sens)
+    y = O.forward_one2many(s)
+    assert rel(A.forward_one2many(s), y) < TOL
+    assert rel(A.adjoint_many2one(y.astype(numpy.complex64)), O.adjoint_many2one(y.astype(numpy.complex64))) < TOL
+    assert rel(A.selfadjoint_one2many2one(s), O.selfadjoint_one2many2one(s)) < TOL
+    gs = A.to_device(s)
+    assert rel(A.to_host(A.s2x(gs)), O.s2x(s)) < TOL
+    assert rel(A.to_host(A.x2s(A.to_device(xb))), O.x2s(xb)) < TOL
+    # batched CG (one alpha/beta for all coils, linalg/solve_hsa.py:555)
+    assert rel(A.solve(y.astype(numpy.complex64), 'cg', maxiter=5), orc.solve_cg(O, y.astype(numpy.complex64), 5)) < 1e-4
+    A.reset_sense()
+    assert rel(A.forward_one2many(s), orc.NUFFT.forward_one2many(_nosense(O), s)) < TOL
+
+
+def _nosense(O):
+    O.reset_sense()
+    return O
+
+
+# ------------------------------------------------------------------------------ config 3 at full size
+@pytest.fixture(scope='module')
+def c3(dev):
+    Nd, Kd, Jd = (128, 128, 128), (256, 256, 256), (6, 6, 6)
+    rng = numpy.random.default_rng(0)
+    om = rng.uniform(-numpy.pi, numpy.pi, (2_000_000, 3))
+    A = make(dev, om, Nd, Kd, Jd)
+    return A, om, Nd, Kd, Jd
+
+
+def test_config3_full_size_against_oracle_subset(c3, dev):
+    """Forward rows are independent and the adjoint is linear in y, so a random subset of the 2M samples
+    is checked exactly against the oracle (CSR over the subset + full 256^3 numpy FFT)."""
+    A, om, Nd, Kd, Jd = c3
+    rng = numpy.random.default_rng(1)
+    x = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    sel = numpy.sort(rng.choice(om.shape[0], 20000, replace=False))
+    O = orc.NUFFT()
+    O.plan(om[sel], Nd, Kd, Jd)
+    kindx, _, k0, perm, tile, sub = A._plan_arrays()
+    assert numpy.array_equal(kindx[sel], O.p.kindx)
+    pfull_k0 = numpy.stack([orc.offset_k0(om[:, d], Jd[d], Kd[d]) for d in range(3)], 1).astype(numpy.int64)
+    assert numpy.array_equal(k0, pfull_k0)
+    assert numpy.array_equal(perm, orc.sort_permutation(pfull_k0, Kd, tile, sub))
+    for v in VARIANTS:
+        A.set_variant(v, v)
+        y = A.forward(x)
+        assert rel(y[sel], O.forward(x)) < TOL
+        ysub = numpy.zeros(om.shape[0], dtype=numpy.complex64)
+        ysub[sel] = (rng.standard_normal(sel.size) + 1j * rng.standard_normal(sel.size)).astype(numpy.complex64)
+        assert rel(A.adjoint(ysub), O.adjoint(ysub[sel])) < TOL
+
+
+def test_config3_properties(c3, dev):
+    """Size-independent properties at full size: linearity, adjointness <Ax,y> = prod(Kd) <x,A^H y>,
+    agreement of the generic and tiled kernels."""
+    A, om, Nd, Kd, Jd = c3
+    rng = numpy.random.default_rng(2)
+    g = lambda shape: torch.from_numpy((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(numpy.complex64)).to(dev)
+    x1, x2, y1 = g(Nd), g(Nd), g((om.shape[0],))
+    A.set_variant(0, 0)
+    f1, f2 = A._forward_device(x1), A._forward_device(x2)
+    f12 = A._forward_device(x1 + 2j * x2)
+    assert (torch.linalg.norm(f12 - (f1 + 2j * f2)) / torch.linalg.norm(f12)).item() < TOL
+    a1 = A._adjoint_device(y1)
+    lhs = torch.vdot(y1, f1)                       # <A x, y> = sum conj(y) (A x)
+    rhs = torch.vdot(a1, x1) * float(numpy.prod(Kd))
+    assert abs(lhs - rhs).item() / abs(lhs).item() < 1e-4
+    A.set_variant(1, 1)
+    f1g, a1g = A._forward_device(x1), A._adjoint_device(y1)
+    assert (torch.linalg.norm(f1g - f1) / torch.linalg.norm(f1)).item() < TOL
+    assert (torch.linalg.norm(a1g - a1) / torch.linalg.norm(a1)).item() < TOL
+    A.set_variant(0, 0)

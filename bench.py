@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the hot path (BASELINE.json: "NUFFT fwd+adj pairs/s at 3D 128^3 J=6;
+interp/gridding HBM GB/s vs peak").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one forward + one adjoint NUFFT (a "pair") on configuration 3 of BASELINE.json:
+Nd 128^3, Kd 256^3, Jd 6^3, M = 2,000,000 uniform random samples, complex64, one coil per GPU.
+At N > 1 (torchrun, one rank per GPU, NCCL) every rank owns one coil of the same trajectory (weak
+scaling: per-GPU work fixed) and the adjoint image is summed with one all-reduce per step, which is
+the only exchange the path has (adjoint_many2one).  Prints ONE JSON line on rank 0.
+
+  value      device-resident pairs/s over all ranks (CUDA events, max over ranks)
+  e2e        the same through the host API NUFFT.forward/adjoint (pinned host buffers, H2D + D2H timed)
+  roofline   dominant kernel (slower of interp / gridding): algorithmic bytes (SURVEY.md 8d:
+             8*K + 12*M*sum(J) + 8*M = 582.2 MB) / CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's numpy/scipy CPU path on a bounded sample
+--impl reference times that CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ND, KD, JD, M = (128, 128, 128), (256, 256, 256), (6, 6, 6), 2_000_000
+WORKLOAD = '3D Nd=128^3 Kd=256^3 Jd=6^3 M=2000000 uniform-random samples, 1 coil per GPU (BASELINE.json configs[2])'
+ALGO_BYTES = 8 * 256 ** 3 + 12 * M * 18 + 8 * M          # interp or gridding, SURVEY.md 8d
+CPU_SAMPLE_M = 100_000
+
+
+def make_om():
+    return numpy.random.default_rng(0).uniform(-numpy.pi, numpy.pi, (M, 3))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference's numpy/scipy implementation), bounded sample
+# ------------------------------------------------------------------------------------------------
+class CpuPath:
+    """Full-size pad/FFT/crop (256^3) + interpolation/gridding on CPU_SAMPLE_M of the 2M samples; the
+    interp/gridding time is scaled by M / CPU_SAMPLE_M (CSR SpMV cost is linear in the rows)."""
+
+    def __init__(self):
+        from oracle import nufft_oracle as orc
+        om = make_om()[:CPU_SAMPLE_M]
+        self.O = orc.NUFFT()
+        self.O.plan(om, ND, KD, JD)
+        rng = numpy.random.default_rng(1)
+        self.x = (rng.standard_normal(ND) + 1j * rng.standard_normal(ND)).astype(numpy.complex64)
+        self.scale = M / CPU_SAMPLE_M
+
+    def pair_seconds(self):
+        O = self.O
+        t = time.perf_counter
+        t0 = t(); k = O.xx2k(O.x2xx(self.x)); t1 = t()
+        y = O.k2y(k); t2 = t()
+        k2 = O.y2k(y.astype(numpy.complex64)); t3 = t()
+        O.xx2x(O.k2xx(k2)); t4 = t()
+        return (t1 - t0) + (t4 - t3) + self.scale * ((t2 - t1) + (t3 - t2))
+
+    @staticmethod
+    def describe():
+        return ('oracle port of the reference numpy/scipy CPU path: full-size scale+pad+fftn(256^3)+ifftn+crop, '
+                'CSR interpolation+gridding on %d of %d samples scaled x%d; single-threaded like the reference '
+                '(numpy.fft + scipy CSR SpMV)' % (CPU_SAMPLE_M, M, M // CPU_SAMPLE_M))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cpu = CpuPath()
+    for _ in range(max(args.warmup, 0)):
+        cpu.pair_seconds()
+    ts = [cpu.pair_seconds() for _ in range(args.steps)]
+    sec = float(numpy.mean(ts))
+    v = 1.0 / sec
+    line = {
+        'impl': 'reference', 'metric': 'NUFFT forward+adjoint pairs/s', 'value': v, 'unit': 'pairs/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64 (f32)', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD},
+        'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': 1, 'cores_available': os.cpu_count(),
+                         'kind': 'port', 'sample': CpuPath.describe()},
+        'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [v.strip() for v in r.split(',')]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(self.NAMES, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(numpy.median(sm)) if sm else None, 'sm_max_mhz': smax,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import pynufft_b200
+    from pynufft_b200 import _lib
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    om = make_om()
+    A = pynufft_b200.NUFFT(dev)
+    t0 = time.perf_counter()
+    A.plan(om, ND, KD, JD)
+    torch.cuda.synchronize()
+    plan_s = time.perf_counter() - t0
+
+    rng = numpy.random.default_rng(100 + rank)
+    x_host = torch.from_numpy((rng.standard_normal(ND) + 1j * rng.standard_normal(ND)).astype(numpy.complex64)).pin_memory()
+    x = x_host.to(dev)
+
+    def step():
+        y = A._forward_device(x)
+        xa = A._adjoint_device(y)
+        if dist is not None:
+            dist.all_reduce(xa)            # adjoint_many2one image sum over the coil shards
+        return xa
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- headline: device-resident pairs ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    time.sleep(0.25)
+    l0 = lib.b200nufft_launch_count()
+    tw0 = time.perf_counter()
+    ms = timed(step, args.steps, 0)
+    tw1 = time.perf_counter()
+    launches = lib.b200nufft_launch_count() - l0
+    clk = clocks.stop(tw0, tw1)
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host API, pinned host buffers, H2D + D2H inside the timed region ----
+    y_host = torch.empty((M,), dtype=torch.complex64).pin_memory()
+    xa_host = torch.empty(ND, dtype=torch.complex64).pin_memory()
+    xn, yn, xan = x_host.numpy(), y_host.numpy(), xa_host.numpy()
+
+    def e2e_step():
+        A.forward(xn, out=yn)
+        A.adjoint(yn, out=xan)
+        if dist is not None:
+            g = xa_host.to(dev, non_blocking=True)
+            dist.all_reduce(g)
+            xa_host.copy_(g)
+    e2e_iters = max(3, min(args.steps, 20))
+    ms_e2e = timed(e2e_step, e2e_iters, 2)
+    e2e_value = world * e2e_iters / (ms_e2e * 1e-3)
+    h2d = x_host.numel() * 8 + y_host.numel() * 8
+    d2h = y_host.numel() * 8 + xa_host.numel() * 8
+
+    # ---- per-kernel times (rank-local, CUDA events on the launch stream) ----
+    P = ctypes_ptr
+    st = lambda: P(torch.cuda.current_stream().cuda_stream)
+    grid = torch.empty((1,) + KD, dtype=torch.complex64, device=dev)
+    yv = torch.empty((M,), dtype=torch.complex64, device=dev)
+    xo = torch.empty(ND, dtype=torch.complex64, device=dev)
+    lib.b200nufft_scale_pad(A._plan, P(x.data_ptr()), P(grid.data_ptr()), 1, 1, 0, None, st())
+    lib.b200nufft_fft(A._plan, P(grid.data_ptr()), 1, 0, st())
+    kit = max(10, args.steps)
+    kern = {}
+    kern['scale_pad'] = timed(lambda: lib.b200nufft_scale_pad(A._plan, P(x.data_ptr()), P(grid.data_ptr()), 1, 1, 0, None, st()), kit, 3) / kit
+    kern['fft'] = timed(lambda: lib.b200nufft_fft(A._plan, P(grid.data_ptr()), 1, 0, st()), kit, 3) / kit
+    # re-create a well-scaled grid (repeated unnormalised FFTs overflow float32)
+    lib.b200nufft_scale_pad(A._plan, P(x.data_ptr()), P(grid.data_ptr()), 1, 1, 0, None, st())
+    lib.b200nufft_fft(A._plan, P(grid.data_ptr()), 1, 0, st())
+    kern['interp'] = timed(lambda: lib.b200nufft_interp(A._plan, P(grid.data_ptr()), P(yv.data_ptr()), 1, st()), kit, 3) / kit
+    kern['gridding_incl_memset'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(yv.data_ptr()), P(grid.data_ptr()), 1, st()), kit, 3) / kit
+    kern['memset_grid'] = timed(lambda: grid.zero_(), kit, 3) / kit
+    kern['crop_scale'] = timed(lambda: lib.b200nufft_crop_scale(A._plan, P(grid.data_ptr()), P(xo.data_ptr()), 1, 1, 0, None, st()), kit, 3) / kit
+    kern['gridding'] = kern['gridding_incl_memset'] - kern['memset_grid']
+    peak, peak_src = measured_peak()
+    dom = 'gridding' if kern['gridding'] >= kern['interp'] else 'interp'
+    achieved = ALGO_BYTES / (kern[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dom)
+    except Exception:
+        pass
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes': ALGO_BYTES,
+                'interp_GBps': ALGO_BYTES / (kern['interp'] * 1e-3) / 1e9,
+                'gridding_GBps': ALGO_BYTES / (kern['gridding'] * 1e-3) / 1e9}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = CpuPath()
+        cpu.pair_seconds()
+        secs = [cpu.pair_seconds() for _ in range(3)]
+        cpu_baseline = {'value': 1.0 / float(numpy.mean(secs)), 'unit': 'pairs/s', 'cores': 1,
+                        'cores_available': os.cpu_count(), 'kind': 'port', 'sample': CpuPath.describe()}
+
+    if rank == 0:
+        line = {
+            'metric': 'NUFFT forward+adjoint pairs/s', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64 (f32)', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'l2_policy': 'working set per step (134 MB grid + 192 MB plan records) exceeds the 126 MB L2',
+                       'parallelism': 'coil-sharded x%d, one all-reduce of the adjoint image per step' % world if world > 1 else 'single GPU',
+                       'plan_seconds': plan_s, 'plan_bytes': int(lib.b200nufft_plan_bytes(A._plan))},
+            'clocks': clk,
+            'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / e2e_iters},
+            'gpu_launches': int(launches),
+            'roofline': roofline,
+            'kernel_ms': kern,
+            'cpu_baseline': cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def ctypes_ptr(v):
+    import ctypes
+    return ctypes.c_void_p(v)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

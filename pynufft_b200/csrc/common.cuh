@@ -106,8 +106,10 @@ struct b200nufft_plan_s {
     float* d_rec = nullptr;         // (M, recw) sorted order
     float* d_sn = nullptr;          // (sum N)
     int* d_bin_start = nullptr;     // (n_bins + 1), n_bins = n_tiles * nsubprod
-    WorkItem* d_work = nullptr;
+    WorkItem* d_work = nullptr;     // interp: per tile
     int n_work = 0;
+    WorkItem* d_gwork = nullptr;    // gridding: per sub-tile (WorkItem.tile = bin id)
+    int n_gwork = 0;
     int n_tiles = 0;
     int n_bins = 0;
     // scratch grids for the compositions

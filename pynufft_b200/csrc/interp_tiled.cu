@@ -1,5 +1,228 @@
-// placeholder: tiled kernels land in the next commit
+// Tiled interpolation (gather) kernel for 3-D, J = 6: the replacement of pELL_spmv_mCoil
+// (src/re_subroutine.py:751-835) on the headline configuration (128^3 / 256^3 / 6^3).
+//
+// One CTA per work item = (16^3 tile of first-neighbour cells, range of bin-sorted samples).
+//  * the 21^3 box of grid values the tile's samples can touch (tile + J-1 halo, periodic wrap)
+//    is staged once into shared memory with cp.async (row pitch 21, plane pitch 446 complex:
+//    the 16 rows read by one half-warp phase then fall into 16 different 8-byte bank pairs);
+//  * sample records are expanded into shared memory in sub-chunks of 256 (tile-relative base
+//    address, complex last-dimension weights with the per-sample phase folded in);
+//  * a warp takes 8 samples at a time: lane l owns footprint row (j0, j1) = divmod(l, 6), reads its
+//    6 contiguous grid values (LDS.64 x6) and multiplies by the warp-uniform last-dim weights
+//    (24 FFMA); rows 32..35 of the 8 samples are packed into one extra pass (4 lanes per
+//    sample); the 8 partial sums are reduced with a transposed butterfly (18 shuffles per 8
+//    samples instead of 80) and scattered to y through the sort permutation.
+// No atomics, no global traffic inside the loop besides the y store.
 #include "common.cuh"
-bool tiled_supported(const Geom& g) { (void)g; return false; }
-int interp_tiled_launch(b200nufft_plan_t, const float2*, float2*, int, cudaStream_t) { return B200_ERR_UNSUPPORTED; }
-int gridding_tiled_launch(b200nufft_plan_t, const float2*, float2*, int, cudaStream_t) { return B200_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TJ = 6;
+constexpr int TT = 16;
+constexpr int BOX = TT + TJ - 1;          // 21
+constexpr int RP = 21;                    // row pitch (complex), odd
+constexpr int PP = 446;                   // plane pitch (complex) >= 21*21, == 6*RP (mod 16)
+constexpr int TILE_ELEMS = BOX * PP;      // 9366
+constexpr int SUBCHUNK = 256;             // samples expanded per pass
+constexpr int SRW = 28;                   // words per expanded record
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int RECW = 24;                  // words per plan record (3 x 6 + 2 + 3 + 1)
+constexpr size_t SMEM_BYTES = TILE_ELEMS * sizeof(float2) + SUBCHUNK * SRW * sizeof(float);
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+__device__ __forceinline__ float2 row_dot(const float2* __restrict__ tp, const float4 A0, const float4 A1,
+                                          const float4 A2) {
+    float2 rs = make_float2(0.f, 0.f);
+    const float2 k0 = tp[0], k1 = tp[1], k2 = tp[2], k3 = tp[3], k4 = tp[4], k5 = tp[5];
+    cfma(rs, make_float2(A0.x, A0.y), k0);
+    cfma(rs, make_float2(A0.z, A0.w), k1);
+    cfma(rs, make_float2(A1.x, A1.y), k2);
+    cfma(rs, make_float2(A1.z, A1.w), k3);
+    cfma(rs, make_float2(A2.x, A2.y), k4);
+    cfma(rs, make_float2(A2.z, A2.w), k5);
+    return rs;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restrict__ rec,
+               const float2* __restrict__ grid, float2* __restrict__ y, int nb) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* tile = reinterpret_cast<float2*>(smem_raw);
+    float* srec = reinterpret_cast<float*>(smem_raw + TILE_ELEMS * sizeof(float2));
+
+    const WorkItem wi = work[blockIdx.x];
+    const int c = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int t = wi.tile;
+    const int q2 = t % g.ntile[2];
+    t /= g.ntile[2];
+    const int q1 = t % g.ntile[1];
+    const int q0 = t / g.ntile[1];
+    const int T0 = q0 * TT, T1 = q1 * TT, T2 = q2 * TT;
+    const float2* gc = grid + (long long)c * g.Kprod;
+
+    // ---- stage the 21^3 box (periodic) ----
+    {
+        const int K0 = g.K[0], K1 = g.K[1], K2 = g.K[2];
+        for (int e = tid; e < BOX * BOX * BOX; e += NTHREADS) {
+            int p = e / (BOX * BOX);
+            int rem = e - p * (BOX * BOX);
+            int r = rem / BOX;
+            int cc = rem - r * BOX;
+            int i0 = T0 + p, i1 = T1 + r, i2 = T2 + cc;
+            while (i0 >= K0) i0 -= K0;
+            while (i1 >= K1) i1 -= K1;
+            while (i2 >= K2) i2 -= K2;
+            cp_async8(tile + p * PP + r * RP + cc, gc + ((long long)i0 * K1 + i1) * K2 + i2);
+        }
+    }
+
+    // ---- per-lane constants ----
+    const int j0l = lane / 6 > 5 ? 5 : lane / 6, j1l = lane % 6;      // rows 0..31
+    const int rowoff = j0l * PP + j1l * RP;
+    const float2 E01 = cmul(g.E[0][j0l], g.E[1][j1l]);
+    const int rr = lane & 3;                                           // rows 32..35 = (5, 2+rr)
+    const int rowoff_r = 5 * PP + (2 + rr) * RP;
+    const float2 E01r = cmul(g.E[0][5], g.E[1][2 + rr]);
+    const int ur = lane >> 2;
+
+    bool first = true;
+    for (int sb = wi.begin; sb < wi.end; sb += SUBCHUNK) {
+        const int ns = min(SUBCHUNK, wi.end - sb);
+        const int nsr = (ns + 7) & ~7;
+        // ---- expand records: [c0[6] c1[6] | a2[6] complex (c2*E2*P) | base | perm | pad2] ----
+        if (tid < nsr) {
+            float4* R4 = reinterpret_cast<float4*>(srec + tid * SRW);
+            if (tid < ns) {
+                const float4* src = reinterpret_cast<const float4*>(rec + (long long)(sb + tid) * RECW);
+                const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3),
+                             v4 = __ldg(src + 4), v5 = __ldg(src + 5);
+                R4[0] = v0;
+                R4[1] = v1;
+                R4[2] = v2;
+                const float c2[6] = {v3.x, v3.y, v3.z, v3.w, v4.x, v4.y};
+                const float2 P = make_float2(v4.z, v4.w);
+                float2 a2[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    float2 e = cmul(g.E[2][j], P);
+                    a2[j] = make_float2(c2[j] * e.x, c2[j] * e.y);
+                }
+                R4[3] = make_float4(a2[0].x, a2[0].y, a2[1].x, a2[1].y);
+                R4[4] = make_float4(a2[2].x, a2[2].y, a2[3].x, a2[3].y);
+                R4[5] = make_float4(a2[4].x, a2[4].y, a2[5].x, a2[5].y);
+                const int ks0 = __float_as_int(v5.x), ks1 = __float_as_int(v5.y), ks2 = __float_as_int(v5.z);
+                const int base = (ks0 - T0) * PP + (ks1 - T1) * RP + (ks2 - T2);
+                R4[6] = make_float4(__int_as_float(base), v5.w, 0.f, 0.f);
+            } else {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) R4[q] = z;
+                R4[6] = make_float4(__int_as_float(0), __int_as_float(-1), 0.f, 0.f);
+            }
+        }
+        if (first) { cp_async_wait_all(); first = false; }
+        __syncthreads();
+
+        // ---- main loop: 8 samples per warp pass ----
+        for (int b = warp; b < (nsr >> 3); b += NWARPS) {
+            float2 acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float* R = srec + (b * 8 + u) * SRW;
+                const int base = __float_as_int(R[24]);
+                const float w01 = R[j0l] * R[6 + j1l];
+                const float4 A0 = *reinterpret_cast<const float4*>(R + 12);
+                const float4 A1 = *reinterpret_cast<const float4*>(R + 16);
+                const float4 A2 = *reinterpret_cast<const float4*>(R + 20);
+                const float2 rs = row_dot(tile + base + rowoff, A0, A1, A2);
+                const float2 tt = cmul(rs, E01);
+                acc[u] = make_float2(tt.x * w01, tt.y * w01);
+            }
+            {   // rows 32..35 of the 8 samples: lane -> (sample ur, row 32 + rr)
+                const float* R = srec + (b * 8 + ur) * SRW;
+                const int base = __float_as_int(R[24]);
+                const float w01 = R[5] * R[6 + 2 + rr];
+                const float4 A0 = *reinterpret_cast<const float4*>(R + 12);
+                const float4 A1 = *reinterpret_cast<const float4*>(R + 16);
+                const float4 A2 = *reinterpret_cast<const float4*>(R + 20);
+                const float2 rs = row_dot(tile + base + rowoff_r, A0, A1, A2);
+                const float2 tt = cmul(rs, E01r);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (ur == u) {
+                        acc[u].x = fmaf(tt.x, w01, acc[u].x);
+                        acc[u].y = fmaf(tt.y, w01, acc[u].y);
+                    }
+                }
+            }
+            // ---- transposed butterfly: 8 values x 32 lanes -> 8 sums ----
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool hi = lane & 16;
+                const float2 send = hi ? acc[u] : acc[u + 4];
+                const float2 keep = hi ? acc[u + 4] : acc[u];
+                acc[u].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 16);
+                acc[u].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 16);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const bool hi = lane & 8;
+                const float2 send = hi ? acc[u] : acc[u + 2];
+                const float2 keep = hi ? acc[u + 2] : acc[u];
+                acc[u].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 8);
+                acc[u].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 8);
+            }
+            {
+                const bool hi = lane & 4;
+                const float2 send = hi ? acc[0] : acc[1];
+                const float2 keep = hi ? acc[1] : acc[0];
+                acc[0].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 4);
+                acc[0].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 4);
+            }
+            acc[0].x += __shfl_xor_sync(0xffffffffu, acc[0].x, 2);
+            acc[0].y += __shfl_xor_sync(0xffffffffu, acc[0].y, 2);
+            acc[0].x += __shfl_xor_sync(0xffffffffu, acc[0].x, 1);
+            acc[0].y += __shfl_xor_sync(0xffffffffu, acc[0].y, 1);
+            if ((lane & 3) == 0) {
+                const int sid = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                const int s = b * 8 + sid;
+                if (s < ns) {
+                    const int m = __float_as_int(srec[s * SRW + 25]);
+                    y[(long long)m * nb + c] = acc[0];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+bool tiled_supported(const Geom& g) {
+    if (g.ndim != 3 || g.recw != RECW) return false;
+    for (int d = 0; d < 3; ++d)
+        if (g.J[d] != TJ || g.tile[d] != TT || g.sub[d] != 8) return false;
+    return true;
+}
+
+int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        configured = true;
+    }
+    if (p->n_work == 0) return B200_OK;
+    dim3 gr(p->n_work, nb);
+    k_interp_tiled<<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_rec, grid, y, nb);
+    LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -342,6 +342,24 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             PLAN_TRY(cudaStreamSynchronize(st));
             p->bytes += sizeof(WorkItem) * work.size();
         }
+        // gridding: one item per non-empty sub-tile bin (chunks of GCHUNK), heaviest first
+        const int GCHUNK = 4096;
+        std::vector<WorkItem> gwork;
+        for (int b = 0; b < p->n_bins; ++b) {
+            int s0 = h_bin_start[b], e = h_bin_start[b + 1];
+            for (int s = s0; s < e; s += GCHUNK) gwork.push_back(WorkItem{b, s, std::min(e, s + GCHUNK), 0});
+        }
+        std::stable_sort(gwork.begin(), gwork.end(), [](const WorkItem& a, const WorkItem& b) {
+            return (a.end - a.begin) > (b.end - b.begin);
+        });
+        p->n_gwork = (int)gwork.size();
+        if (p->n_gwork > 0) {
+            PLAN_TRY(cudaMalloc(&p->d_gwork, sizeof(WorkItem) * gwork.size()));
+            PLAN_TRY(cudaMemcpyAsync(p->d_gwork, gwork.data(), sizeof(WorkItem) * gwork.size(),
+                                     cudaMemcpyHostToDevice, st));
+            PLAN_TRY(cudaStreamSynchronize(st));
+            p->bytes += sizeof(WorkItem) * gwork.size();
+        }
     }
 #undef PLAN_TRY
     *out = p;
@@ -358,6 +376,7 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_sn);
     cudaFree(p->d_bin_start);
     cudaFree(p->d_work);
+    cudaFree(p->d_gwork);
     cudaFree(p->d_grid);
     cudaFree(p->d_xin);
     cudaFree(p->d_yio);

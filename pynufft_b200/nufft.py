@@ -329,25 +329,35 @@ class NUFFT:
 
     # ------------------------------------------------------------------ host API (numpy in / out)
     def _host_c64(self, a, shape_prefix, what):
-        a = numpy.ascontiguousarray(numpy.asarray(a).astype(self.dtype))
+        a = numpy.ascontiguousarray(numpy.asarray(a, dtype=self.dtype))     # no copy if already complex64 C-order
         if tuple(a.shape[:len(shape_prefix)]) != tuple(shape_prefix) or a.ndim > len(shape_prefix) + 1:
             raise ValueError('%s has shape %s, expected %s(+batch)' % (what, a.shape, tuple(shape_prefix)))
         return a
 
-    def forward(self, x):
+    def _host_out(self, out, shape, what):
+        if out is None:
+            return numpy.empty(shape, dtype=self.dtype)
+        if not (isinstance(out, numpy.ndarray) and out.dtype == self.dtype and out.flags.c_contiguous
+                and tuple(out.shape) == tuple(shape)):
+            raise ValueError('%s must be a C-contiguous complex64 array of shape %s' % (what, tuple(shape)))
+        return out
+
+    def forward(self, x, out=None):
+        """Host forward NUFFT (reference: _forward_host).  `out` may be a preallocated (pinned) array."""
         self._require_plan()
         x = self._host_c64(x, self.Nd, 'x')
         nb = x.shape[-1] if x.ndim == self.ndims + 1 else 1
-        y = numpy.empty((self.M, nb) if x.ndim == self.ndims + 1 else (self.M,), dtype=self.dtype)
+        y = self._host_out(out, (self.M, nb) if x.ndim == self.ndims + 1 else (self.M,), 'out')
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b200nufft_forward_host(self._plan, x.ctypes.data, y.ctypes.data, nb, _stream()))
         return y
 
-    def adjoint(self, y):
+    def adjoint(self, y, out=None):
+        """Host adjoint NUFFT (reference: _adjoint_host)."""
         self._require_plan()
         y = self._host_c64(y, (self.M,), 'y')
         nb = y.shape[-1] if y.ndim == 2 else 1
-        x = numpy.empty(tuple(self.Nd) + ((nb,) if y.ndim == 2 else ()), dtype=self.dtype)
+        x = self._host_out(out, tuple(self.Nd) + ((nb,) if y.ndim == 2 else ()), 'out')
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b200nufft_adjoint_host(self._plan, y.ctypes.data, x.ctypes.data, nb, _stream()))
         return x

@@ -76,6 +76,10 @@ struct Geom {
     long long Kstride[MAXD];  // C-order element stride of the grid
     int recw;           // words (4 B) per sample record, multiple of 4
     float2 E[MAXD][MAXJ];     // E_d[j] = exp(+i gam_d (N_d-1)/2 (j+1)), j = 0..J_d-1
+    // last-dimension phase split used by the tiled kernels: E_last[j] = Fl[cc] * Gl[rel] with box column
+    // cc = rel + j:  Fl[cc] = exp(+i s (cc+1)), Gl[rel] = exp(-i s rel), s = gam (N-1)/2 of the last dim
+    float2 Fl[24];
+    float2 Gl[16];
 };
 
 // Per-dimension float64 constants of the min-max interpolator (plan kernels only).

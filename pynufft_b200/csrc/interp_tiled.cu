@@ -3,15 +3,19 @@
 //
 // One CTA per work item = (16^3 tile of first-neighbour cells, range of bin-sorted samples).
 //  * the 21^3 box of grid values the tile's samples can touch (tile + J-1 halo, periodic wrap)
-//    is staged once into shared memory with cp.async (row pitch 21, plane pitch 446 complex:
-//    the 16 rows read by one half-warp phase then fall into 16 different 8-byte bank pairs);
-//  * sample records are expanded into shared memory in sub-chunks of 256 (tile-relative base
-//    address, complex last-dimension weights with the per-sample phase folded in);
+//    is staged once into shared memory, one warp per box row (coalesced 168-byte row reads);
+//    while staging, every value is multiplied by the last-dimension phase Fl[column], which
+//    turns the last-dimension interpolation weights into REAL numbers (the remaining
+//    per-sample phase Gl[rel] is folded into the sample's phase P);
+//    layout: row pitch 21, plane pitch 446 complex -> the 16 rows read by one half-warp phase fall
+//    into 16 different 8-byte bank pairs;
+//  * sample records are expanded into shared memory in sub-chunks (tile-relative base address,
+//    P * Gl[rel]);
 //  * a warp takes 8 samples at a time: lane l owns footprint row (j0, j1) = divmod(l, 6), reads its
-//    6 contiguous grid values (LDS.64 x6) and multiplies by the warp-uniform last-dim weights
-//    (24 FFMA); rows 32..35 of the 8 samples are packed into one extra pass (4 lanes per
-//    sample); the 8 partial sums are reduced with a transposed butterfly (18 shuffles per 8
-//    samples instead of 80) and scattered to y through the sort permutation.
+//    6 contiguous grid values (LDS.64 x6) and contracts them with the warp-uniform real
+//    last-dim weights (12 FFMA); rows 32..35 of the 8 samples are packed into one extra pass
+//    (4 lanes per sample); the 8 partial sums are reduced with a transposed butterfly
+//    (18 shuffles per 8 samples instead of 80) and scattered to y through the sort permutation.
 // No atomics, no global traffic inside the loop besides the y store.
 #include "common.cuh"
 
@@ -24,30 +28,30 @@ constexpr int RP = 21;                    // row pitch (complex), odd
 constexpr int PP = 446;                   // plane pitch (complex) >= 21*21, == 6*RP (mod 16)
 constexpr int TILE_ELEMS = BOX * PP;      // 9366
 constexpr int SUBCHUNK = 256;             // samples expanded per pass
-constexpr int SRW = 28;                   // words per expanded record
-constexpr int NTHREADS = 256;
+constexpr int SRW = 24;                   // words per expanded record
+constexpr int NTHREADS = 384;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int RECW = 24;                  // words per plan record (3 x 6 + 2 + 3 + 1)
 constexpr size_t SMEM_BYTES = TILE_ELEMS * sizeof(float2) + SUBCHUNK * SRW * sizeof(float);
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
+// expanded record: [c0[6] | c1[6] | c2[6] | base, perm | P'.re, P'.im | pad2]
+//                   0       6       12      18    19     20     21
 
-__device__ __forceinline__ float2 row_dot(const float2* __restrict__ tp, const float4 A0, const float4 A1,
-                                          const float4 A2) {
-    float2 rs = make_float2(0.f, 0.f);
+__device__ __forceinline__ float2 row_dot(const float2* __restrict__ tp, const float4 C0, const float2 C1) {
     const float2 k0 = tp[0], k1 = tp[1], k2 = tp[2], k3 = tp[3], k4 = tp[4], k5 = tp[5];
-    cfma(rs, make_float2(A0.x, A0.y), k0);
-    cfma(rs, make_float2(A0.z, A0.w), k1);
-    cfma(rs, make_float2(A1.x, A1.y), k2);
-    cfma(rs, make_float2(A1.z, A1.w), k3);
-    cfma(rs, make_float2(A2.x, A2.y), k4);
-    cfma(rs, make_float2(A2.z, A2.w), k5);
+    float2 rs;
+    rs.x = C0.x * k0.x;
+    rs.y = C0.x * k0.y;
+    rs.x = fmaf(C0.y, k1.x, rs.x);
+    rs.y = fmaf(C0.y, k1.y, rs.y);
+    rs.x = fmaf(C0.z, k2.x, rs.x);
+    rs.y = fmaf(C0.z, k2.y, rs.y);
+    rs.x = fmaf(C0.w, k3.x, rs.x);
+    rs.y = fmaf(C0.w, k3.y, rs.y);
+    rs.x = fmaf(C1.x, k4.x, rs.x);
+    rs.y = fmaf(C1.x, k4.y, rs.y);
+    rs.x = fmaf(C1.y, k5.x, rs.x);
+    rs.y = fmaf(C1.y, k5.y, rs.y);
     return rs;
 }
 
@@ -69,19 +73,22 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
     const int T0 = q0 * TT, T1 = q1 * TT, T2 = q2 * TT;
     const float2* gc = grid + (long long)c * g.Kprod;
 
-    // ---- stage the 21^3 box (periodic) ----
+    // ---- stage the 21^3 box (periodic), one warp per row, times Fl[column] ----
     {
         const int K0 = g.K[0], K1 = g.K[1], K2 = g.K[2];
-        for (int e = tid; e < BOX * BOX * BOX; e += NTHREADS) {
-            int p = e / (BOX * BOX);
-            int rem = e - p * (BOX * BOX);
-            int r = rem / BOX;
-            int cc = rem - r * BOX;
-            int i0 = T0 + p, i1 = T1 + r, i2 = T2 + cc;
+        int i2 = T2 + lane;
+        while (i2 >= K2) i2 -= K2;
+        const float2 F = g.Fl[lane < BOX ? lane : 0];
+#pragma unroll 4
+        for (int row = warp; row < BOX * BOX; row += NWARPS) {
+            const int p = row / BOX, r = row - p * BOX;
+            int i0 = T0 + p, i1 = T1 + r;
             while (i0 >= K0) i0 -= K0;
             while (i1 >= K1) i1 -= K1;
-            while (i2 >= K2) i2 -= K2;
-            cp_async8(tile + p * PP + r * RP + cc, gc + ((long long)i0 * K1 + i1) * K2 + i2);
+            if (lane < BOX) {
+                const float2 v = __ldg(gc + ((long long)i0 * K1 + i1) * K2 + i2);
+                tile[p * PP + r * RP + lane] = cmul(v, F);
+            }
         }
     }
 
@@ -94,11 +101,10 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
     const float2 E01r = cmul(g.E[0][5], g.E[1][2 + rr]);
     const int ur = lane >> 2;
 
-    bool first = true;
     for (int sb = wi.begin; sb < wi.end; sb += SUBCHUNK) {
         const int ns = min(SUBCHUNK, wi.end - sb);
         const int nsr = (ns + 7) & ~7;
-        // ---- expand records: [c0[6] c1[6] | a2[6] complex (c2*E2*P) | base | perm | pad2] ----
+        // ---- expand records ----
         if (tid < nsr) {
             float4* R4 = reinterpret_cast<float4*>(srec + tid * SRW);
             if (tid < ns) {
@@ -108,28 +114,19 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
                 R4[0] = v0;
                 R4[1] = v1;
                 R4[2] = v2;
-                const float c2[6] = {v3.x, v3.y, v3.z, v3.w, v4.x, v4.y};
-                const float2 P = make_float2(v4.z, v4.w);
-                float2 a2[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    float2 e = cmul(g.E[2][j], P);
-                    a2[j] = make_float2(c2[j] * e.x, c2[j] * e.y);
-                }
-                R4[3] = make_float4(a2[0].x, a2[0].y, a2[1].x, a2[1].y);
-                R4[4] = make_float4(a2[2].x, a2[2].y, a2[3].x, a2[3].y);
-                R4[5] = make_float4(a2[4].x, a2[4].y, a2[5].x, a2[5].y);
+                R4[3] = v3;
                 const int ks0 = __float_as_int(v5.x), ks1 = __float_as_int(v5.y), ks2 = __float_as_int(v5.z);
                 const int base = (ks0 - T0) * PP + (ks1 - T1) * RP + (ks2 - T2);
-                R4[6] = make_float4(__int_as_float(base), v5.w, 0.f, 0.f);
+                R4[4] = make_float4(v4.x, v4.y, __int_as_float(base), v5.w);
+                const float2 Pp = cmul(make_float2(v4.z, v4.w), g.Gl[ks2 - T2]);
+                R4[5] = make_float4(Pp.x, Pp.y, 0.f, 0.f);
             } else {
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < 6; ++q) R4[q] = z;
-                R4[6] = make_float4(__int_as_float(0), __int_as_float(-1), 0.f, 0.f);
+                R4[4] = make_float4(0.f, 0.f, __int_as_float(0), __int_as_float(-1));
             }
         }
-        if (first) { cp_async_wait_all(); first = false; }
         __syncthreads();
 
         // ---- main loop: 8 samples per warp pass ----
@@ -138,23 +135,21 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float* R = srec + (b * 8 + u) * SRW;
-                const int base = __float_as_int(R[24]);
+                const int base = __float_as_int(R[18]);
                 const float w01 = R[j0l] * R[6 + j1l];
-                const float4 A0 = *reinterpret_cast<const float4*>(R + 12);
-                const float4 A1 = *reinterpret_cast<const float4*>(R + 16);
-                const float4 A2 = *reinterpret_cast<const float4*>(R + 20);
-                const float2 rs = row_dot(tile + base + rowoff, A0, A1, A2);
+                const float4 C0 = *reinterpret_cast<const float4*>(R + 12);
+                const float2 C1 = *reinterpret_cast<const float2*>(R + 16);
+                const float2 rs = row_dot(tile + base + rowoff, C0, C1);
                 const float2 tt = cmul(rs, E01);
                 acc[u] = make_float2(tt.x * w01, tt.y * w01);
             }
             {   // rows 32..35 of the 8 samples: lane -> (sample ur, row 32 + rr)
                 const float* R = srec + (b * 8 + ur) * SRW;
-                const int base = __float_as_int(R[24]);
+                const int base = __float_as_int(R[18]);
                 const float w01 = R[5] * R[6 + 2 + rr];
-                const float4 A0 = *reinterpret_cast<const float4*>(R + 12);
-                const float4 A1 = *reinterpret_cast<const float4*>(R + 16);
-                const float4 A2 = *reinterpret_cast<const float4*>(R + 20);
-                const float2 rs = row_dot(tile + base + rowoff_r, A0, A1, A2);
+                const float4 C0 = *reinterpret_cast<const float4*>(R + 12);
+                const float2 C1 = *reinterpret_cast<const float2*>(R + 16);
+                const float2 rs = row_dot(tile + base + rowoff_r, C0, C1);
                 const float2 tt = cmul(rs, E01r);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -196,8 +191,9 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
                 const int sid = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
                 const int s = b * 8 + sid;
                 if (s < ns) {
-                    const int m = __float_as_int(srec[s * SRW + 25]);
-                    y[(long long)m * nb + c] = acc[0];
+                    const float* R = srec + s * SRW;
+                    const int m = __float_as_int(R[19]);
+                    y[(long long)m * nb + c] = cmul(make_float2(R[20], R[21]), acc[0]);
                 }
             }
         }

@@ -260,6 +260,10 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         double s = pc.gam[d] * ((double)g.N[d] - 1.0) / 2.0;
         for (int j = 0; j < g.J[d]; ++j)
             g.E[d][j] = make_float2((float)cos(s * (j + 1)), (float)sin(s * (j + 1)));
+        if (d == ndim - 1) {
+            for (int t = 0; t < 24; ++t) g.Fl[t] = make_float2((float)cos(s * (t + 1)), (float)sin(s * (t + 1)));
+            for (int t = 0; t < 16; ++t) g.Gl[t] = make_float2((float)cos(s * t), (float)-sin(s * t));
+        }
     }
 
 #define PLAN_TRY(expr)                                                      \

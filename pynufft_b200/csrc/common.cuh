@@ -116,6 +116,9 @@ struct b200nufft_plan_s {
     int n_gwork = 0;
     int n_tiles = 0;
     int n_bins = 0;
+    // bin-sorted copy of the data for the tiled gridding kernel (16-byte slots)
+    float4* d_ys = nullptr;
+    int ys_nb = 0;
     // scratch grids for the compositions
     float2* d_grid = nullptr;
     int grid_nb = 0;

@@ -3,15 +3,21 @@
 //
 // Shared-memory float atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN), so the accumulation is
 // made conflict-free by construction instead:
-//  * one WARP per work item = (8^3 sub-tile of first-neighbour cells, range of bin-sorted samples);
-//    the warp owns a private 13^3 accumulation box in shared memory (row pitch 13, plane pitch 174
+//  * a pre-pass gathers y into bin-sorted order (ys[i] = y[perm[i]]), so that everything the
+//    main kernel reads is contiguous;
+//  * one WARP per work item = (8^3 sub-tile of first-neighbour cells, range of bin-sorted samples).
+//    The warp owns a private 13^3 accumulation box in shared memory (row pitch 13, plane pitch 174
 //    complex -> the 16 rows of a half-warp phase hit 16 different bank pairs);
+//  * sample records and sorted data arrive in 16-sample chunks by TMA bulk copies
+//    (cp.async.bulk + mbarrier), double buffered, and are fixed up in place by 16 lanes;
 //  * samples are processed one at a time: lane l owns footprint row (j0, j1) = divmod(l, 6) and does
-//    a plain read-modify-write of its 6 contiguous elements (LDS.64 / 4 FFMA / STS.64 each); the
+//    a plain read-modify-write of its 6 contiguous elements (LDS.64 / 2 FFMA / STS.64 each: the
+//    last-dimension phase is factored out of the box, so the last-dim weights are real); the
 //    remaining rows 32..35 (24 elements) take one element per lane.  All lanes of one step touch
 //    distinct addresses and no other warp shares the box -> no atomics, no races;
-//  * when the range is done the box is flushed once to the global grid with vector reductions
-//    (REDG.E.ADD.F32x2), because the halos of neighbouring boxes overlap.
+//  * when the range is done the box is multiplied by the last-dimension phase conj(Fl[column]) and
+//    flushed once to the global grid with vector reductions (REDG.E.ADD.F32x2), because the halos
+//    of neighbouring boxes overlap.
 // The 2*M*prod(J) global float atomics of the reference become ~4.3 * prod(Kd) vector REDs.
 #include "common.cuh"
 
@@ -23,23 +29,68 @@ constexpr int GBOX = GT + GJ - 1;        // 13
 constexpr int GRP = 13;                  // row pitch (complex), odd
 constexpr int GPP = 174;                 // plane pitch >= 13*13, == 6*GRP (mod 16)
 constexpr int GBOX_ELEMS = GBOX * GPP;   // 2262
-constexpr int GBATCH = 8;                // samples expanded per pass
-constexpr int GSRW = 28;                 // words per expanded record
+constexpr int GB = 16;                   // samples per chunk
 constexpr int RECW = 24;
-constexpr size_t GSMEM_BYTES = GBOX_ELEMS * sizeof(float2) + GBATCH * GSRW * sizeof(float);
+constexpr int CHUNK_BYTES = GB * RECW * 4 + GB * 16;      // records + sorted data (16-byte slots: TMA alignment)
+constexpr size_t GSMEM_BYTES = GBOX_ELEMS * sizeof(float2) + 2 * CHUNK_BYTES + 16;
 
-__device__ __forceinline__ void rmw(float2* p, float2 b, float2 w) {
-    float2 v = *p;
-    cfma(v, b, w);
-    *p = v;
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ int wrap2(int i, int K) {
+    i -= (i >= K) ? K : 0;
+    i -= (i >= K) ? K : 0;
+    return i;
+}
+
+// ys[c][i] = (y[perm[i], c], 0, 0)   -- one 16-byte slot per sample so that any range is TMA-aligned
+__global__ void k_gather_sorted(const float* __restrict__ rec, int recw, int perm_word, long long M,
+                                const float2* __restrict__ y, float4* __restrict__ ys, int nb) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int c = blockIdx.y;
+    const int m = __float_as_int(rec[i * recw + perm_word]);
+    const float2 v = y[(long long)m * nb + c];
+    ys[(long long)c * M + i] = make_float4(v.x, v.y, 0.f, 0.f);
+}
+
+struct SampleRegs {
+    float4 C0;      // c2[0..3]
+    float4 C1Y;     // c2[4], c2[5], Y'.re, Y'.im
+    int base;
+    float w01;      // rows 0..31
+    float wr;       // rows 32..35: c0[5] * c1[2+rr] * c2[j2r]
+};
 
 __global__ void __launch_bounds__(32)
 k_gridding_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restrict__ rec,
-                 const float2* __restrict__ y, float2* __restrict__ grid, int nb) {
+                 const float4* __restrict__ ys, long long M, float2* __restrict__ grid) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* box = reinterpret_cast<float2*>(smem_raw);
-    float* srec = reinterpret_cast<float*>(smem_raw + GBOX_ELEMS * sizeof(float2));
+    unsigned char* cbuf = smem_raw + GBOX_ELEMS * sizeof(float2);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(cbuf + 2 * CHUNK_BYTES);
 
     const WorkItem wi = work[blockIdx.x];
     const int c = blockIdx.y;
@@ -57,8 +108,29 @@ k_gridding_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restr
     const int q1 = t % g.ntile[1];
     const int q0 = t / g.ntile[1];
     const int O0 = q0 * g.tile[0] + s0 * GT, O1 = q1 * g.tile[1] + s1 * GT, O2 = q2 * g.tile[2] + s2 * GT;
+    const float4* ysc = ys + (long long)c * M;
 
-    for (int e = lane; e < GBOX_ELEMS; e += 32) box[e] = make_float2(0.f, 0.f);
+    const int nchunks = (wi.end - wi.begin + GB - 1) / GB;
+    auto issue = [&](int k) {      // lane 0 only
+        const int s = wi.begin + k * GB;
+        const int ns = min(GB, wi.end - s);
+        unsigned char* dst = cbuf + (k & 1) * CHUNK_BYTES;
+        mbar_expect(&mbar[k & 1], (unsigned)(ns * (RECW * 4 + 16)));
+        tma_bulk(dst, rec + (long long)s * RECW, (unsigned)(ns * RECW * 4), &mbar[k & 1]);
+        tma_bulk(dst + GB * RECW * 4, ysc + s, (unsigned)(ns * 16), &mbar[k & 1]);
+    };
+    if (lane == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) issue(0);
+
+    {   // zero the box (16-byte stores; GBOX_ELEMS is even)
+        float4* b4 = reinterpret_cast<float4*>(box);
+        for (int e = lane; e < GBOX_ELEMS / 2; e += 32) b4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     // per-lane constants
     const int j0l = lane / 6 > 5 ? 5 : lane / 6, j1l = lane % 6;                // rows 0..31
@@ -69,77 +141,97 @@ k_gridding_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restr
     const int remoff = 5 * GPP + (2 + rr) * GRP + j2r;
     float2 E01rc = cmul(g.E[0][5], g.E[1][2 + rr]);
     E01rc.y = -E01rc.y;
+    const bool remlane = lane < 24;
     __syncwarp();
 
-    for (int s0i = wi.begin; s0i < wi.end; s0i += GBATCH) {
-        const int ns = min(GBATCH, wi.end - s0i);
-        // ---- expand records: [c0[6] c1[6] | b2[6] complex = c2*conj(E2)*conj(P)*y | base | pad3] ----
+    for (int k = 0; k < nchunks; ++k) {
+        const int ns = min(GB, wi.end - (wi.begin + k * GB));
+        if (k + 1 < nchunks) {
+            fence_proxy_async();         // generic-proxy writes (fix-up of chunk k-1) before the async-proxy overwrite
+            __syncwarp();
+            if (lane == 0) issue(k + 1);
+        }
+        mbar_wait(&mbar[k & 1], (unsigned)((k >> 1) & 1));
+        float* srec = reinterpret_cast<float*>(cbuf + (k & 1) * CHUNK_BYTES);
+        // ---- in-place fix-up, one sample per lane: [.. c2[4] c2[5] | P | ks0 ks1 ks2 perm] ->
+        //      [.. c2[4] c2[5] | Y'.re Y'.im | base ...],  Y' = conj(P * Gl[rel2]) * y
         if (lane < ns) {
-            float4* R4 = reinterpret_cast<float4*>(srec + lane * GSRW);
-            const float4* src = reinterpret_cast<const float4*>(rec + (long long)(s0i + lane) * RECW);
-            const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3),
-                         v4 = __ldg(src + 4), v5 = __ldg(src + 5);
-            R4[0] = v0;
-            R4[1] = v1;
-            R4[2] = v2;
-            const float c2[6] = {v3.x, v3.y, v3.z, v3.w, v4.x, v4.y};
-            const float2 P = make_float2(v4.z, v4.w);
-            const int m = __float_as_int(v5.w);
-            const float2 yv = cmulc(P, y[(long long)m * nb + c]);                // conj(P) * y
-            float2 b2[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                float2 e = cmulc(g.E[2][j], yv);                                // conj(E2) * conj(P) * y
-                b2[j] = make_float2(c2[j] * e.x, c2[j] * e.y);
-            }
-            R4[3] = make_float4(b2[0].x, b2[0].y, b2[1].x, b2[1].y);
-            R4[4] = make_float4(b2[2].x, b2[2].y, b2[3].x, b2[3].y);
-            R4[5] = make_float4(b2[4].x, b2[4].y, b2[5].x, b2[5].y);
+            float* R = srec + lane * RECW;
+            const float2 Pr = *reinterpret_cast<const float2*>(R + 18);
+            const float4 v5 = *reinterpret_cast<const float4*>(R + 20);
+            const float2 yv = *reinterpret_cast<const float2*>(srec + GB * RECW + 4 * lane);
             const int ks0 = __float_as_int(v5.x), ks1 = __float_as_int(v5.y), ks2 = __float_as_int(v5.z);
             const int base = (ks0 - O0) * GPP + (ks1 - O1) * GRP + (ks2 - O2);
-            R4[6] = make_float4(__int_as_float(base), 0.f, 0.f, 0.f);
+            const float2 Pp = cmul(Pr, g.Gl[ks2 - O2]);
+            const float2 Yp = cmulc(Pp, yv);
+            *reinterpret_cast<float2*>(R + 18) = Yp;
+            R[20] = __int_as_float(base);
         }
         __syncwarp();
+
+        auto load = [&](int u) {
+            SampleRegs s;
+            const float* R = srec + u * RECW;
+            s.C0 = *reinterpret_cast<const float4*>(R + 12);
+            s.C1Y = *reinterpret_cast<const float4*>(R + 16);
+            s.base = __float_as_int(R[20]);
+            s.w01 = R[j0l] * R[6 + j1l];
+            s.wr = R[5] * R[6 + 2 + rr] * R[12 + j2r];
+            return s;
+        };
+        SampleRegs cur = load(0);
         for (int u = 0; u < ns; ++u) {
-            const float* R = srec + u * GSRW;
-            const int base = __float_as_int(R[24]);
-            const float w01 = R[j0l] * R[6 + j1l];
-            const float4 B0 = *reinterpret_cast<const float4*>(R + 12);
-            const float4 B1 = *reinterpret_cast<const float4*>(R + 16);
-            const float4 B2 = *reinterpret_cast<const float4*>(R + 20);
-            const float2 wl = make_float2(E01c.x * w01, E01c.y * w01);
-            float2* tp = box + base + rowoff;
-            rmw(tp + 0, make_float2(B0.x, B0.y), wl);
-            rmw(tp + 1, make_float2(B0.z, B0.w), wl);
-            rmw(tp + 2, make_float2(B1.x, B1.y), wl);
-            rmw(tp + 3, make_float2(B1.z, B1.w), wl);
-            rmw(tp + 4, make_float2(B2.x, B2.y), wl);
-            rmw(tp + 5, make_float2(B2.z, B2.w), wl);
-            if (lane < 24) {                                                     // rows 32..35
-                const float wr = R[5] * R[6 + 2 + rr];
-                const float2 br = *reinterpret_cast<const float2*>(R + 12 + 2 * j2r);
-                rmw(box + base + remoff, br, make_float2(E01rc.x * wr, E01rc.y * wr));
+            SampleRegs nxt = cur;
+            if (u + 1 < ns) nxt = load(u + 1);           // prefetch the next sample's weights
+            const float2 Yp = make_float2(cur.C1Y.z, cur.C1Y.w);
+            float2 wl = cmul(E01c, Yp);
+            wl.x *= cur.w01;
+            wl.y *= cur.w01;
+            float2* tp = box + cur.base + rowoff;
+            float2 v0 = tp[0], v1 = tp[1], v2 = tp[2], v3 = tp[3], v4 = tp[4], v5 = tp[5];
+            v0.x = fmaf(cur.C0.x, wl.x, v0.x); v0.y = fmaf(cur.C0.x, wl.y, v0.y);
+            v1.x = fmaf(cur.C0.y, wl.x, v1.x); v1.y = fmaf(cur.C0.y, wl.y, v1.y);
+            v2.x = fmaf(cur.C0.z, wl.x, v2.x); v2.y = fmaf(cur.C0.z, wl.y, v2.y);
+            v3.x = fmaf(cur.C0.w, wl.x, v3.x); v3.y = fmaf(cur.C0.w, wl.y, v3.y);
+            v4.x = fmaf(cur.C1Y.x, wl.x, v4.x); v4.y = fmaf(cur.C1Y.x, wl.y, v4.y);
+            v5.x = fmaf(cur.C1Y.y, wl.x, v5.x); v5.y = fmaf(cur.C1Y.y, wl.y, v5.y);
+            tp[0] = v0; tp[1] = v1; tp[2] = v2; tp[3] = v3; tp[4] = v4; tp[5] = v5;
+            if (remlane) {                                // rows 32..35, one element per lane
+                float2 wlr = cmul(E01rc, Yp);
+                float2* e = box + cur.base + remoff;
+                float2 v = *e;
+                v.x = fmaf(cur.wr, wlr.x, v.x);
+                v.y = fmaf(cur.wr, wlr.y, v.y);
+                *e = v;
             }
             __syncwarp();
+            cur = nxt;
         }
     }
 
-    // ---- flush the box (periodic) ----
+    // ---- flush: box * conj(Fl[column]) -> global grid (periodic), vector REDs ----
     {
         const int K0 = g.K[0], K1 = g.K[1], K2 = g.K[2];
+        const int KK = K1 * K2;
         float2* gc = grid + (long long)c * g.Kprod;
-        for (int e = lane; e < GBOX * GBOX * GBOX; e += 32) {
-            int p = e / (GBOX * GBOX);
-            int rem = e - p * (GBOX * GBOX);
-            int r = rem / GBOX;
-            int cc = rem - r * GBOX;
-            const float2 v = box[p * GPP + r * GRP + cc];
-            if (v.x != 0.f || v.y != 0.f) {
-                int i0 = O0 + p, i1 = O1 + r, i2 = O2 + cc;
-                while (i0 >= K0) i0 -= K0;
-                while (i1 >= K1) i1 -= K1;
-                while (i2 >= K2) i2 -= K2;
-                atomicAdd(gc + ((long long)i0 * K1 + i1) * K2 + i2, v);
+        // lane -> (row parity h, column cc): 26 lanes busy, two rows per step
+        const int h = lane >= GBOX ? 1 : 0;
+        const int cc = lane - h * GBOX;
+        const bool act = lane < 2 * GBOX;
+        float2 Fc = g.Fl[act ? cc : 0];
+        Fc.y = -Fc.y;
+        const int i2 = wrap2(O2 + (act ? cc : 0), K2);
+        for (int p = 0; p < GBOX; ++p) {
+            const int pb = wrap2(O0 + p, K0) * KK + i2;
+#pragma unroll 4
+            for (int r = h; r < GBOX; r += 2) {
+                if (act) {
+                    const float2 v = box[p * GPP + r * GRP + cc];
+                    if (v.x != 0.f || v.y != 0.f) {
+                        const int i1 = wrap2(O1 + r, K1);
+                        atomicAdd(gc + (unsigned)(pb + i1 * K2), cmul(v, Fc));
+                    }
+                }
             }
         }
     }
@@ -155,8 +247,20 @@ int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int
         configured = true;
     }
     if (p->n_gwork == 0) return B200_OK;
+    // sorted copy of the data (plan-owned scratch)
+    if (p->ys_nb < nb) {
+        if (p->d_ys) { CUDA_TRY(cudaFree(p->d_ys)); p->d_ys = nullptr; p->ys_nb = 0; }
+        CUDA_TRY(cudaMalloc(&p->d_ys, sizeof(float4) * p->M * nb));
+        p->ys_nb = nb;
+    }
+    {
+        const int TB = 256;
+        dim3 gr((unsigned)((p->M + TB - 1) / TB), nb);
+        k_gather_sorted<<<gr, TB, 0, st>>>(p->d_rec, p->g.recw, p->g.sumJ + 2 + p->g.ndim, p->M, y, p->d_ys, nb);
+        LAUNCH_CHECK();
+    }
     dim3 gr(p->n_gwork, nb);
-    k_gridding_tiled<<<gr, 32, GSMEM_BYTES, st>>>(p->g, p->d_gwork, p->d_rec, y, grid, nb);
+    k_gridding_tiled<<<gr, 32, GSMEM_BYTES, st>>>(p->g, p->d_gwork, p->d_rec, p->d_ys, p->M, grid);
     LAUNCH_CHECK();
     return B200_OK;
 }

@@ -1,16 +1,16 @@
 // Tiled interpolation (gather) kernel for 3-D, J = 6: the replacement of pELL_spmv_mCoil
 // (src/re_subroutine.py:751-835) on the headline configuration (128^3 / 256^3 / 6^3).
 //
-// One CTA per work item = (16^3 tile of first-neighbour cells, range of bin-sorted samples).
-//  * the 21^3 box of grid values the tile's samples can touch (tile + J-1 halo, periodic wrap)
-//    is staged once into shared memory, one warp per box row (coalesced 168-byte row reads);
-//    while staging, every value is multiplied by the last-dimension phase Fl[column], which
-//    turns the last-dimension interpolation weights into REAL numbers (the remaining
-//    per-sample phase Gl[rel] is folded into the sample's phase P);
-//    layout: row pitch 21, plane pitch 446 complex -> the 16 rows read by one half-warp phase fall
-//    into 16 different 8-byte bank pairs;
-//  * sample records are expanded into shared memory in sub-chunks (tile-relative base address,
-//    P * Gl[rel]);
+// One CTA per work item = (8 x 16 x 16 slab of first-neighbour cells, range of bin-sorted samples).
+//  * the 13 x 21 x 21 box of grid values the slab's samples can touch (slab + J-1 halo, periodic
+//    wrap) is staged once into shared memory, one warp per box row (coalesced 168-byte row
+//    reads).  Every staged value is multiplied by the last-dimension phase Fl[column], which turns
+//    the last-dimension interpolation weights into REAL numbers (the remaining per-sample phase
+//    Gl[rel] is folded into the sample's phase P).  Layout: row pitch 21, plane pitch 446 complex
+//    -> the 16 rows read by one half-warp phase fall into 16 different 8-byte bank pairs;
+//  * the plan's sample records (96 B each, contiguous in bin order) arrive in shared memory by ONE
+//    TMA bulk copy per sub-chunk (cp.async.bulk + mbarrier) and are fixed up in place
+//    (tile-relative base address, P * Gl[rel]);
 //  * a warp takes 8 samples at a time: lane l owns footprint row (j0, j1) = divmod(l, 6), reads its
 //    6 contiguous grid values (LDS.64 x6) and contracts them with the warp-uniform real
 //    last-dim weights (12 FFMA); rows 32..35 of the 8 samples are packed into one extra pass
@@ -22,20 +22,47 @@
 namespace {
 
 constexpr int TJ = 6;
-constexpr int TT = 16;
+constexpr int TT = 16;                    // tile edge (dims 1, 2)
+constexpr int TS = 8;                     // slab thickness (dim 0)
 constexpr int BOX = TT + TJ - 1;          // 21
+constexpr int NPL = TS + TJ - 1;          // 13 planes
 constexpr int RP = 21;                    // row pitch (complex), odd
 constexpr int PP = 446;                   // plane pitch (complex) >= 21*21, == 6*RP (mod 16)
-constexpr int TILE_ELEMS = BOX * PP;      // 9366
-constexpr int SUBCHUNK = 256;             // samples expanded per pass
-constexpr int SRW = 24;                   // words per expanded record
-constexpr int NTHREADS = 384;
+constexpr int TILE_ELEMS = NPL * PP;      // 5798
+constexpr int SUBCHUNK = 256;             // samples per record sub-chunk
+constexpr int SRW = 24;                   // words per record
+constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int RECW = 24;                  // words per plan record (3 x 6 + 2 + 3 + 1)
-constexpr size_t SMEM_BYTES = TILE_ELEMS * sizeof(float2) + SUBCHUNK * SRW * sizeof(float);
+constexpr size_t SMEM_BYTES = TILE_ELEMS * sizeof(float2) + SUBCHUNK * SRW * sizeof(float) + 16;
 
-// expanded record: [c0[6] | c1[6] | c2[6] | base, perm | P'.re, P'.im | pad2]
-//                   0       6       12      18    19     20     21
+// record after fix-up: [c0[6] | c1[6] | c2[6] | base, perm | P'.re, P'.im | (ks2, perm)]
+//                       0       6       12      18    19     20     21
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ float2 row_dot(const float2* __restrict__ tp, const float4 C0, const float2 C1) {
     const float2 k0 = tp[0], k1 = tp[1], k2 = tp[2], k3 = tp[3], k4 = tp[4], k5 = tp[5];
@@ -55,12 +82,19 @@ __device__ __forceinline__ float2 row_dot(const float2* __restrict__ tp, const f
     return rs;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+__device__ __forceinline__ int wrap2(int i, int K) {   // i in [0, 3K)
+    i -= (i >= K) ? K : 0;
+    i -= (i >= K) ? K : 0;
+    return i;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3)
 k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restrict__ rec,
                const float2* __restrict__ grid, float2* __restrict__ y, int nb) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* tile = reinterpret_cast<float2*>(smem_raw);
     float* srec = reinterpret_cast<float*>(smem_raw + TILE_ELEMS * sizeof(float2));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + TILE_ELEMS * sizeof(float2) + SUBCHUNK * SRW * sizeof(float));
 
     const WorkItem wi = work[blockIdx.x];
     const int c = blockIdx.y;
@@ -70,24 +104,55 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
     t /= g.ntile[2];
     const int q1 = t % g.ntile[1];
     const int q0 = t / g.ntile[1];
-    const int T0 = q0 * TT, T1 = q1 * TT, T2 = q2 * TT;
+    const int T0 = q0 * TT + wi.pad, T1 = q1 * TT, T2 = q2 * TT;
     const float2* gc = grid + (long long)c * g.Kprod;
 
-    // ---- stage the 21^3 box (periodic), one warp per row, times Fl[column] ----
+    // ---- records of the first sub-chunk: one TMA bulk copy ----
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    unsigned phase = 0;
+    if (tid == 0) {
+        const int ns0 = min(SUBCHUNK, wi.end - wi.begin);
+        tma_bulk_load(srec, rec + (long long)wi.begin * RECW, (unsigned)(ns0 * RECW * sizeof(float)), mbar);
+    }
+
+    // ---- stage the 13 x 21 x 21 box (periodic) times Fl[column]: one warp per row, 7 loads in flight ----
     {
+        // warp w owns rows r = w, w+8, w+16 of every plane; 32-bit element offsets (prod(Kd) < 2^31)
         const int K0 = g.K[0], K1 = g.K[1], K2 = g.K[2];
-        int i2 = T2 + lane;
-        while (i2 >= K2) i2 -= K2;
-        const float2 F = g.Fl[lane < BOX ? lane : 0];
-#pragma unroll 4
-        for (int row = warp; row < BOX * BOX; row += NWARPS) {
-            const int p = row / BOX, r = row - p * BOX;
-            int i0 = T0 + p, i1 = T1 + r;
-            while (i0 >= K0) i0 -= K0;
-            while (i1 >= K1) i1 -= K1;
-            if (lane < BOX) {
-                const float2 v = __ldg(gc + ((long long)i0 * K1 + i1) * K2 + i2);
-                tile[p * PP + r * RP + lane] = cmul(v, F);
+        const int KK = K1 * K2;
+        const bool act = lane < BOX;
+        const int i2 = wrap2(T2 + (act ? lane : 0), K2);
+        const float2 F = g.Fl[act ? lane : 0];
+        constexpr int RQ = (BOX + NWARPS - 1) / NWARPS;   // 3
+        int roff[RQ], soff[RQ];
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            const int r = warp + NWARPS * q;
+            const bool ok = act && r < BOX;
+            roff[q] = ok ? wrap2(T1 + (r < BOX ? r : 0), K1) * K2 + i2 : -1;
+            soff[q] = r * RP + lane;
+        }
+        constexpr int PU = 4;                             // planes per batch -> 12 loads in flight per lane
+#pragma unroll
+        for (int p0 = 0; p0 < NPL; p0 += PU) {
+            float2 v[PU][RQ];
+#pragma unroll
+            for (int pp = 0; pp < PU; ++pp) {
+                if (p0 + pp < NPL) {
+                    const int pb = wrap2(T0 + p0 + pp, K0) * KK;
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q)
+                        if (roff[q] >= 0) v[pp][q] = __ldg(gc + (unsigned)(pb + roff[q]));
+                }
+            }
+#pragma unroll
+            for (int pp = 0; pp < PU; ++pp) {
+                if (p0 + pp < NPL) {
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q)
+                        if (roff[q] >= 0) tile[(p0 + pp) * PP + soff[q]] = cmul(v[pp][q], F);
+                }
             }
         }
     }
@@ -104,30 +169,34 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
     for (int sb = wi.begin; sb < wi.end; sb += SUBCHUNK) {
         const int ns = min(SUBCHUNK, wi.end - sb);
         const int nsr = (ns + 7) & ~7;
-        // ---- expand records ----
+        if (sb != wi.begin) {
+            // previous sub-chunk fully consumed (trailing __syncthreads); order generic writes before the TMA write
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) tma_bulk_load(srec, rec + (long long)sb * RECW, (unsigned)(ns * RECW * sizeof(float)), mbar);
+        }
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        // ---- in-place fix-up: [.. | P.re P.im | ks0 ks1 ks2 perm] -> [.. | base perm | P'.re P'.im | ..] ----
         if (tid < nsr) {
-            float4* R4 = reinterpret_cast<float4*>(srec + tid * SRW);
+            float* R = srec + tid * SRW;
             if (tid < ns) {
-                const float4* src = reinterpret_cast<const float4*>(rec + (long long)(sb + tid) * RECW);
-                const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3),
-                             v4 = __ldg(src + 4), v5 = __ldg(src + 5);
-                R4[0] = v0;
-                R4[1] = v1;
-                R4[2] = v2;
-                R4[3] = v3;
+                const float2 Pr = *reinterpret_cast<const float2*>(R + 18);
+                const float4 v5 = *reinterpret_cast<const float4*>(R + 20);
                 const int ks0 = __float_as_int(v5.x), ks1 = __float_as_int(v5.y), ks2 = __float_as_int(v5.z);
                 const int base = (ks0 - T0) * PP + (ks1 - T1) * RP + (ks2 - T2);
-                R4[4] = make_float4(v4.x, v4.y, __int_as_float(base), v5.w);
-                const float2 Pp = cmul(make_float2(v4.z, v4.w), g.Gl[ks2 - T2]);
-                R4[5] = make_float4(Pp.x, Pp.y, 0.f, 0.f);
+                const float2 Pp = cmul(Pr, g.Gl[ks2 - T2]);
+                *reinterpret_cast<float2*>(R + 18) = make_float2(__int_as_float(base), v5.w);
+                *reinterpret_cast<float2*>(R + 20) = Pp;
             } else {
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4* R4 = reinterpret_cast<float4*>(R);
 #pragma unroll
                 for (int q = 0; q < 6; ++q) R4[q] = z;
-                R4[4] = make_float4(0.f, 0.f, __int_as_float(0), __int_as_float(-1));
+                R[19] = __int_as_float(-1);
             }
         }
-        __syncthreads();
+        __syncthreads();    // tile staged + records fixed up
 
         // ---- main loop: 8 samples per warp pass ----
         for (int b = warp; b < (nsr >> 3); b += NWARPS) {
@@ -206,7 +275,7 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
 bool tiled_supported(const Geom& g) {
     if (g.ndim != 3 || g.recw != RECW) return false;
     for (int d = 0; d < 3; ++d)
-        if (g.J[d] != TJ || g.tile[d] != TT || g.sub[d] != 8) return false;
+        if (g.J[d] != TJ || g.tile[d] != TT || g.sub[d] != TS) return false;
     return true;
 }
 

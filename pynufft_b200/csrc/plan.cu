@@ -329,11 +329,18 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
 
     // work list for the tiled kernels: non-empty tiles, split into chunks, heaviest first
     {
+        // interp: a tile is cut along dim 0 into nsub[0] slabs (sub-tiles with the same s0 are
+        // contiguous in the sort order); WorkItem.pad = first plane of the slab inside the tile.
         const int CHUNK = 1024;
         std::vector<WorkItem> work;
+        const int slabs = g.nsub[0];
+        const int per_slab = g.nsubprod / slabs;
         for (int t = 0; t < p->n_tiles; ++t) {
-            int b = h_bin_start[t * g.nsubprod], e = h_bin_start[(t + 1) * g.nsubprod];
-            for (int s = b; s < e; s += CHUNK) work.push_back(WorkItem{t, s, std::min(e, s + CHUNK), 0});
+            for (int h = 0; h < slabs; ++h) {
+                int b = h_bin_start[t * g.nsubprod + h * per_slab], e = h_bin_start[t * g.nsubprod + (h + 1) * per_slab];
+                for (int s = b; s < e; s += CHUNK)
+                    work.push_back(WorkItem{t, s, std::min(e, s + CHUNK), h * g.sub[0]});
+            }
         }
         std::stable_sort(work.begin(), work.end(), [](const WorkItem& a, const WorkItem& b) {
             return (a.end - a.begin) > (b.end - b.begin);
@@ -381,6 +388,7 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_bin_start);
     cudaFree(p->d_work);
     cudaFree(p->d_gwork);
+    cudaFree(p->d_ys);
     cudaFree(p->d_grid);
     cudaFree(p->d_xin);
     cudaFree(p->d_yio);

@@ -59,6 +59,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+__device__ __forceinline__ float2 lds64(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+
 __device__ __forceinline__ int wrap2(int i, int K) {
     i -= (i >= K) ? K : 0;
     i -= (i >= K) ? K : 0;
@@ -142,6 +151,7 @@ k_gridding_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restr
     float2 E01rc = cmul(g.E[0][5], g.E[1][2 + rr]);
     E01rc.y = -E01rc.y;
     const bool remlane = lane < 24;
+    const unsigned box_s = smem_u32(box);
     __syncwarp();
 
     for (int k = 0; k < nchunks; ++k) {
@@ -179,34 +189,41 @@ k_gridding_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restr
             s.wr = R[5] * R[6 + 2 + rr] * R[12 + j2r];
             return s;
         };
-        SampleRegs cur = load(0);
-        for (int u = 0; u < ns; ++u) {
-            SampleRegs nxt = cur;
-            if (u + 1 < ns) nxt = load(u + 1);           // prefetch the next sample's weights
+        auto accumulate = [&](const SampleRegs& cur) {
             const float2 Yp = make_float2(cur.C1Y.z, cur.C1Y.w);
             float2 wl = cmul(E01c, Yp);
             wl.x *= cur.w01;
             wl.y *= cur.w01;
-            float2* tp = box + cur.base + rowoff;
-            float2 v0 = tp[0], v1 = tp[1], v2 = tp[2], v3 = tp[3], v4 = tp[4], v5 = tp[5];
+            const unsigned a = box_s + (unsigned)(cur.base + rowoff) * 8u;
+            float2 v0 = lds64(a), v1 = lds64(a + 8), v2 = lds64(a + 16), v3 = lds64(a + 24), v4 = lds64(a + 32),
+                   v5 = lds64(a + 40);
             v0.x = fmaf(cur.C0.x, wl.x, v0.x); v0.y = fmaf(cur.C0.x, wl.y, v0.y);
             v1.x = fmaf(cur.C0.y, wl.x, v1.x); v1.y = fmaf(cur.C0.y, wl.y, v1.y);
             v2.x = fmaf(cur.C0.z, wl.x, v2.x); v2.y = fmaf(cur.C0.z, wl.y, v2.y);
             v3.x = fmaf(cur.C0.w, wl.x, v3.x); v3.y = fmaf(cur.C0.w, wl.y, v3.y);
             v4.x = fmaf(cur.C1Y.x, wl.x, v4.x); v4.y = fmaf(cur.C1Y.x, wl.y, v4.y);
             v5.x = fmaf(cur.C1Y.y, wl.x, v5.x); v5.y = fmaf(cur.C1Y.y, wl.y, v5.y);
-            tp[0] = v0; tp[1] = v1; tp[2] = v2; tp[3] = v3; tp[4] = v4; tp[5] = v5;
+            sts64(a, v0); sts64(a + 8, v1); sts64(a + 16, v2); sts64(a + 24, v3); sts64(a + 32, v4); sts64(a + 40, v5);
             if (remlane) {                                // rows 32..35, one element per lane
-                float2 wlr = cmul(E01rc, Yp);
-                float2* e = box + cur.base + remoff;
-                float2 v = *e;
+                const float2 wlr = cmul(E01rc, Yp);
+                const unsigned e = box_s + (unsigned)(cur.base + remoff) * 8u;
+                float2 v = lds64(e);
                 v.x = fmaf(cur.wr, wlr.x, v.x);
                 v.y = fmaf(cur.wr, wlr.y, v.y);
-                *e = v;
+                sts64(e, v);
             }
             __syncwarp();
-            cur = nxt;
+        };
+        // two samples per trip, registers ping-pong (the next sample's weights load while this one accumulates)
+        SampleRegs ra = load(0), rb;
+        int u = 0;
+        for (; u + 2 <= ns; u += 2) {
+            rb = load(u + 1);
+            accumulate(ra);
+            if (u + 2 < ns) ra = load(u + 2);
+            accumulate(rb);
         }
+        if (u < ns) accumulate(ra);
     }
 
     // ---- flush: box * conj(Fl[column]) -> global grid (periodic), vector REDs ----
@@ -221,18 +238,23 @@ k_gridding_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restr
         float2 Fc = g.Fl[act ? cc : 0];
         Fc.y = -Fc.y;
         const int i2 = wrap2(O2 + (act ? cc : 0), K2);
+        int goff[7];                      // global row offsets of rows h, h+2, ..
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const int r = h + 2 * q;
+            goff[q] = (act && r < GBOX) ? wrap2(O1 + (r < GBOX ? r : 0), K1) * K2 + i2 : -1;
+        }
+        const unsigned lane_s = box_s + (unsigned)(h * GRP + cc) * 8u;
         for (int p = 0; p < GBOX; ++p) {
-            const int pb = wrap2(O0 + p, K0) * KK + i2;
-#pragma unroll 4
-            for (int r = h; r < GBOX; r += 2) {
-                if (act) {
-                    const float2 v = box[p * GPP + r * GRP + cc];
-                    if (v.x != 0.f || v.y != 0.f) {
-                        const int i1 = wrap2(O1 + r, K1);
-                        atomicAdd(gc + (unsigned)(pb + i1 * K2), cmul(v, Fc));
-                    }
-                }
-            }
+            float2* gp = gc + (unsigned)(wrap2(O0 + p, K0) * KK);
+            const unsigned ps = lane_s + (unsigned)(p * GPP) * 8u;
+            float2 v[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                if (goff[q] >= 0) v[q] = lds64(ps + q * 2 * GRP * 8);
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                if (goff[q] >= 0) atomicAdd(gp + goff[q], cmul(v[q], Fc));
         }
     }
 }

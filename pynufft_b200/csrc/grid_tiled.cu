@@ -75,12 +75,12 @@ __device__ __forceinline__ int wrap2(int i, int K) {
 }
 
 // ys[c][i] = (y[perm[i], c], 0, 0)   -- one 16-byte slot per sample so that any range is TMA-aligned
-__global__ void k_gather_sorted(const float* __restrict__ rec, int recw, int perm_word, long long M,
+__global__ void k_gather_sorted(const int* __restrict__ perm, long long M,
                                 const float2* __restrict__ y, float4* __restrict__ ys, int nb) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= M) return;
     const int c = blockIdx.y;
-    const int m = __float_as_int(rec[i * recw + perm_word]);
+    const int m = perm[i];
     const float2 v = y[(long long)m * nb + c];
     ys[(long long)c * M + i] = make_float4(v.x, v.y, 0.f, 0.f);
 }
@@ -278,7 +278,7 @@ int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int
     {
         const int TB = 256;
         dim3 gr((unsigned)((p->M + TB - 1) / TB), nb);
-        k_gather_sorted<<<gr, TB, 0, st>>>(p->d_rec, p->g.recw, p->g.sumJ + 2 + p->g.ndim, p->M, y, p->d_ys, nb);
+        k_gather_sorted<<<gr, TB, 0, st>>>(p->d_perm, p->M, y, p->d_ys, nb);
         LAUNCH_CHECK();
     }
     dim3 gr(p->n_gwork, nb);

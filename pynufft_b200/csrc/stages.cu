@@ -32,71 +32,75 @@ __global__ void k_x2xx(Geom g, const float* __restrict__ sn, const float2* __res
 }
 
 // ------------------------------------------------------------------------------------------
-// scale_pad: one thread per PAIR of grid elements along the last axis (float4 store) when the
-// last extents are even, else one element per thread.  blockIdx.y = coil.
+// scale_pad: one (threadIdx.y) thread row per grid row (all leading coordinates fixed); the
+// leading-index decode is uniform per row and 32-bit; every grid element is written (zeros
+// outside the image corner), VEC = 2 -> float4 stores.  blockIdx.y = coil.
 // ------------------------------------------------------------------------------------------
+#define SP_TX 64
+#define SP_TY 4
 template <int VEC>
-__global__ void k_scale_pad(Geom g, const float* __restrict__ sn, const float2* __restrict__ x,
-                            float2* __restrict__ grid, int nb, int apply_sn, int x_single,
-                            const float2* __restrict__ sens) {
+__global__ void __launch_bounds__(SP_TX * SP_TY)
+k_scale_pad(Geom g, const float* __restrict__ sn, const float2* __restrict__ x, float2* __restrict__ grid,
+            int nb, int apply_sn, int x_single, const float2* __restrict__ sens, int nrows) {
     const int c = blockIdx.y;
-    long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * VEC;
-    if (e >= g.Kprod) return;
-    // decode grid index -> image index; inside iff every coordinate < N_d
+    const int row = blockIdx.x * SP_TY + threadIdx.y;
+    if (row >= nrows) return;
     const int dl = g.ndim - 1;
-    long long rem = e;
-    long long n = 0;
+    const int KL = g.K[dl], NL = g.N[dl];
+    // decode the leading coordinates of this row
+    int rem = row, n = 0;
     bool inside = true;
     float sbase = 1.f;
-    long long nstride = g.Nprod;
-    for (int d = 0; d < dl; ++d) {
-        nstride /= g.N[d];
-        int i = (int)(rem / g.Kstride[d]);
-        rem -= i * g.Kstride[d];
-        if (i >= g.N[d]) {
-            inside = false;
-        } else {
+    for (int d = dl - 1; d >= 0; --d) {
+        const int i = rem % g.K[d];
+        rem /= g.K[d];
+        if (i >= g.N[d]) inside = false;
+    }
+    if (inside) {
+        rem = row;
+        int nstride = 1;
+        for (int d = dl - 1; d >= 0; --d) {
+            const int i = rem % g.K[d];
+            rem /= g.K[d];
             n += i * nstride;
+            nstride *= g.N[d];
             if (apply_sn) sbase *= sn[g.snoff[d] + i];
         }
     }
-    const int ilast = (int)rem;
-    float2 v[VEC];
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) v[q] = make_float2(0.f, 0.f);
-    if (inside) {
+    float2* dst = grid + (long long)c * g.Kprod + (long long)row * KL;
+    const long long nrow = (long long)n * NL;
+    for (int i2 = threadIdx.x * VEC; i2 < KL; i2 += SP_TX * VEC) {
+        float2 v[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
-            if (ilast + q < g.N[dl]) {
-                long long nn = n + ilast + q;
+            v[q] = make_float2(0.f, 0.f);
+            if (inside && i2 + q < NL) {
+                const long long nn = nrow + i2 + q;
                 float2 xv = x_single ? x[nn] : x[nn * nb + c];
                 if (sens) xv = cmul(xv, sens[nn * nb + c]);
-                float f = apply_sn ? sbase * sn[g.snoff[dl] + ilast + q] : 1.f;
+                const float f = apply_sn ? sbase * sn[g.snoff[dl] + i2 + q] : 1.f;
                 v[q] = make_float2(xv.x * f, xv.y * f);
             }
         }
-    }
-    float2* dst = grid + (long long)c * g.Kprod + e;
-    if (VEC == 2) {
-        *reinterpret_cast<float4*>(dst) = make_float4(v[0].x, v[0].y, v[VEC - 1].x, v[VEC - 1].y);
-    } else {
-        dst[0] = v[0];
+        if (VEC == 2) {
+            *reinterpret_cast<float4*>(dst + i2) = make_float4(v[0].x, v[0].y, v[VEC - 1].x, v[VEC - 1].y);
+        } else {
+            dst[i2] = v[0];
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // crop_scale
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long image_to_grid(const Geom& g, long long n, float* s_out,
-                                                   const float* __restrict__ sn) {
-    long long idx = 0;
+__device__ __forceinline__ int image_to_grid(const Geom& g, int n, float* s_out, const float* __restrict__ sn) {
+    // 32-bit decode (prod(Nd) <= prod(Kd) < 2^31), last dimension first
+    int idx = 0;
     float s = 1.f;
-    long long nstride = g.Nprod;
-    for (int d = 0; d < g.ndim; ++d) {
-        nstride /= g.N[d];
-        int i = (int)(n / nstride);
-        n -= i * nstride;
-        idx += i * g.Kstride[d];
+    for (int d = g.ndim - 1; d >= 0; --d) {
+        const int i = n % g.N[d];
+        n /= g.N[d];
+        idx += i * (int)g.Kstride[d];
         s *= sn[g.snoff[d] + i];
     }
     *s_out = s;
@@ -107,10 +111,10 @@ __global__ void k_crop_scale(Geom g, const float* __restrict__ sn, const float2*
                              float2* __restrict__ x, int nb, int mode, float scale) {
     long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (gid >= g.Nprod * nb) return;
-    long long n = gid / nb;
-    int c = (int)(gid - n * nb);
+    const int n = (int)(gid / nb);
+    const int c = (int)(gid - (long long)n * nb);
     float s;
-    long long idx = image_to_grid(g, n, &s, sn);
+    const int idx = image_to_grid(g, n, &s, sn);
     float f = scale * (mode == 1 ? s : (mode == 2 ? 1.f / s : 1.f));
     float2 v = grid[(long long)c * g.Kprod + idx];
     x[gid] = make_float2(v.x * f, v.y * f);
@@ -119,10 +123,10 @@ __global__ void k_crop_scale(Geom g, const float* __restrict__ sn, const float2*
 __global__ void k_crop_combine(Geom g, const float* __restrict__ sn, const float2* __restrict__ grid,
                                float2* __restrict__ x, int nb, int mode, float scale,
                                const float2* __restrict__ sens) {
-    long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n >= g.Nprod) return;
     float s;
-    long long idx = image_to_grid(g, n, &s, sn);
+    const int idx = image_to_grid(g, (int)n, &s, sn);
     float f = scale * (mode == 1 ? s : (mode == 2 ? 1.f / s : 1.f)) / (float)nb;   // mean over coils
     float2 acc = make_float2(0.f, 0.f);
     for (int c = 0; c < nb; ++c) {
@@ -163,20 +167,19 @@ extern "C" int b200nufft_scale_pad(b200nufft_plan_t p, const b200_c64* x, b200_c
     ARG_CHECK(p && x && grid && nb >= 1 && nb <= 65535, "scale_pad: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
     const Geom& g = p->g;
-    const int TB = 256;
     const int dl = g.ndim - 1;
-    bool vec2 = (g.K[dl] % 2 == 0) && (g.N[dl] % 2 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+    const int nrows = (int)(g.Kprod / g.K[dl]);
+    bool vec2 = (g.K[dl] % 2 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+    dim3 blk(SP_TX, SP_TY);
+    dim3 gr((unsigned)((nrows + SP_TY - 1) / SP_TY), nb);
     if (vec2) {
-        long long nthr = g.Kprod / 2;
-        dim3 gr((unsigned)((nthr + TB - 1) / TB), nb);
-        k_scale_pad<2><<<gr, TB, 0, as_stream(stream)>>>(g, p->d_sn, reinterpret_cast<const float2*>(x),
-                                                         reinterpret_cast<float2*>(grid), nb, apply_sn, x_single,
-                                                         reinterpret_cast<const float2*>(sens));
+        k_scale_pad<2><<<gr, blk, 0, as_stream(stream)>>>(g, p->d_sn, reinterpret_cast<const float2*>(x),
+                                                          reinterpret_cast<float2*>(grid), nb, apply_sn, x_single,
+                                                          reinterpret_cast<const float2*>(sens), nrows);
     } else {
-        dim3 gr((unsigned)((g.Kprod + TB - 1) / TB), nb);
-        k_scale_pad<1><<<gr, TB, 0, as_stream(stream)>>>(g, p->d_sn, reinterpret_cast<const float2*>(x),
-                                                         reinterpret_cast<float2*>(grid), nb, apply_sn, x_single,
-                                                         reinterpret_cast<const float2*>(sens));
+        k_scale_pad<1><<<gr, blk, 0, as_stream(stream)>>>(g, p->d_sn, reinterpret_cast<const float2*>(x),
+                                                          reinterpret_cast<float2*>(grid), nb, apply_sn, x_single,
+                                                          reinterpret_cast<const float2*>(sens), nrows);
     }
     LAUNCH_CHECK();
     return B200_OK;

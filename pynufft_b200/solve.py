@@ -36,58 +36,88 @@ def _flat(view):
     return cm
 
 
+class CudaVectorOps:
+    """The fused CUDA vector kernels of csrc/solver.cu behind a tiny interface (so that the CG driver's
+    control flow -- including where the all-reduces sit -- can be exercised on CPU by the tests)."""
+
+    def __init__(self, lib):
+        self.L = lib
+
+    def scalars(self, device):
+        return torch.zeros(6, dtype=torch.float64, device=device)
+
+    def cg_init(self, b, Ax, r, p, rsold):
+        _lib.check(self.L.b200nufft_cg_init(_ptr(b), _ptr(Ax), _ptr(r), _ptr(p), _ptr(rsold), r.numel(), _stream()))
+
+    def dotc(self, a, b, out):
+        out.zero_()
+        _lib.check(self.L.b200nufft_dotc(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()))
+
+    def update_xr(self, x, r, p, Ap, rsold, pAp, rsnew):
+        rsnew.zero_()
+        _lib.check(self.L.b200nufft_cg_update_xr(_ptr(x), _ptr(r), _ptr(p), _ptr(Ap), _ptr(rsold), _ptr(pAp),
+                                                 _ptr(rsnew), x.numel(), _stream()))
+
+    def update_p(self, p, r, rsnew, rsold):
+        _lib.check(self.L.b200nufft_cg_update_p(_ptr(p), _ptr(r), _ptr(rsnew), _ptr(rsold), p.numel(), _stream()))
+
+
+def cg_kspace(G, b, maxiter, ops, allreduce=None):
+    """
+    The k-space CG of linalg/solve_device.py:351-461 on flat complex64 vectors:
+    x0 = b, r = b - G x, exactly `maxiter` steps, one alpha/beta for everything in the vector
+    (all coils, linalg/solve_hsa.py:555).  `G(v)` applies interp^H interp to a flat vector and returns a
+    flat vector; `allreduce(t)` (optional) sums a 2-element float64 tensor over the coil shards.
+    Returns x (flat).
+    """
+    x = b.clone()
+    Ax = G(x)
+    r = torch.empty_like(b)
+    p = torch.empty_like(b)
+    sc = ops.scalars(b.device)
+    rsold, pAp, rsnew = sc[0:2], sc[2:4], sc[4:6]
+    ops.cg_init(b, Ax, r, p, rsold)
+    if allreduce is not None:
+        allreduce(rsold)
+    del Ax
+    for _ in range(int(maxiter)):
+        Ap = G(p)
+        ops.dotc(p, Ap, pAp)
+        if allreduce is not None:
+            allreduce(pAp)
+        ops.update_xr(x, r, p, Ap, rsold, pAp, rsnew)
+        if allreduce is not None:
+            allreduce(rsnew)
+        ops.update_p(p, r, rsnew, rsold)
+        rsold.copy_(rsnew)
+        del Ap
+    return x
+
+
 def cg(nufft, gy, maxiter=30, group=None):
-    """k-space CG on G = interp^H interp, x0 = b, exactly `maxiter` steps, then k2xx and /sn."""
+    """k-space CG on G = interp^H interp, x0 = b, exactly `maxiter` steps, then k2xx and /sn
+    (linalg/solve_device.py:351-481).  `group`: process group of the coil shards (pynufft_b200.dist)."""
     L = nufft._lib
-    st = _stream
     allreduce = None
     if group is not None:
         import torch.distributed as dist
         allreduce = lambda t: dist.all_reduce(t, group=group)
+    bview = nufft._y2k_device(gy)
+    batched = bview.dim() == nufft.ndims + 1
+    nd = nufft.ndims
 
-    def G(view):
-        return nufft._y2k_device(nufft._k2y_device(view))
+    def as_view(flat):            # flat coil-major storage -> Kd(+B) view accepted by _k2y_device without a copy
+        return flat.permute(*range(1, nd + 1), 0) if batched else flat
 
-    b = nufft._y2k_device(gy)
-    x = b.clone(memory_format=torch.preserve_format)
-    Ax = G(x)
-    r = torch.empty_like(_flat(b))
-    p_store = torch.empty_like(_flat(b))
-    n = r.numel()
-    # scalars: [rsold(2), pAp(2), rsnew(2)] float64
-    sc = torch.zeros(6, dtype=torch.float64, device=nufft.device)
-    rsold, pAp, rsnew = sc[0:2], sc[2:4], sc[4:6]
-    _lib.check(L.b200nufft_cg_init(_ptr(_flat(b)), _ptr(_flat(Ax)), _ptr(r), _ptr(p_store), _ptr(rsold), n, st()))
-    if allreduce:
-        allreduce(rsold)
-    del Ax
-    xs = _flat(x)
-    # p as a grid view with the same layout as b so that it can be fed to _k2y_device without a copy
-    if b.is_contiguous():
-        p_view = p_store
-    else:
-        nd = b.dim() - 1
-        p_view = p_store.permute(*range(1, nd + 1), 0)
-    for _ in range(maxiter):
-        Ap = G(p_view)
-        pAp.zero_()
-        _lib.check(L.b200nufft_dotc(_ptr(p_store), _ptr(_flat(Ap)), n, _ptr(pAp), st()))
-        if allreduce:
-            allreduce(pAp)
-        rsnew.zero_()
-        _lib.check(L.b200nufft_cg_update_xr(_ptr(xs), _ptr(r), _ptr(p_store), _ptr(_flat(Ap)), _ptr(rsold),
-                                            _ptr(pAp), _ptr(rsnew), n, st()))
-        if allreduce:
-            allreduce(rsnew)
-        _lib.check(L.b200nufft_cg_update_p(_ptr(p_store), _ptr(r), _ptr(rsnew), _ptr(rsold), n, st()))
-        rsold.copy_(rsnew)
-        del Ap
+    def G(flat):
+        return _flat(nufft._y2k_device(nufft._k2y_device(as_view(flat))))
+
+    xs = cg_kspace(G, _flat(bview), maxiter, CudaVectorOps(L), allreduce)
     # inverse FFT, crop, divide by sn  (solve_device.py:463-480)
-    nb = 1 if x.dim() == nufft.ndims else int(x.shape[-1])
-    x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if x.dim() == nufft.ndims + 1 else ()), dtype=torch.complex64,
-                     device=nufft.device)
-    _lib.check(L.b200nufft_fft(nufft._plan, _ptr(xs), nb, 1, st()))
-    _lib.check(L.b200nufft_crop_scale(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, st()))
+    nb = int(xs.shape[0]) if batched else 1
+    x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=nufft.device)
+    _lib.check(L.b200nufft_fft(nufft._plan, _ptr(xs), nb, 1, _stream()))
+    _lib.check(L.b200nufft_crop_scale(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
     return x2
 
 

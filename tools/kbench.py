@@ -36,6 +36,10 @@ out['gridding_tiled_vs_generic'] = float(torch.linalg.norm(g_til - g_gen) / torc
 out['interp_us'] = timed(lambda: lib.b200nufft_interp(A._plan, P(k.data_ptr()), P(yv.data_ptr()), 1, st()))
 out['gridding_us'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()))
 out['memset_us'] = timed(lambda: grid.zero_())
+A.set_variant(1, 1)
+out['interp_generic_us'] = timed(lambda: lib.b200nufft_interp(A._plan, P(k.data_ptr()), P(yv.data_ptr()), 1, st()), it=5, warm=1)
+out['gridding_generic_us'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()), it=5, warm=1)
+A.set_variant(0, 0)
 out['scale_pad_us'] = timed(lambda: lib.b200nufft_scale_pad(A._plan, P(x.data_ptr()), P(grid.data_ptr()), 1, 1, 0, None, st()))
 out['fft_us'] = timed(lambda: lib.b200nufft_fft(A._plan, P(grid.data_ptr()), 1, 0, st()))
 xo = torch.empty(Nd, dtype=torch.complex64, device='cuda')

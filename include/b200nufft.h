@@ -90,7 +90,10 @@ int b200nufft_x2xx(b200nufft_plan_t plan, const b200_c64* in, b200_c64* out, int
 int b200nufft_scale_pad(b200nufft_plan_t plan, const b200_c64* x, b200_c64* grid, int nb,
                         int apply_sn, int x_single, const b200_c64* sens, void* stream);
 /* fft : in-place c2c FFT of nb coil-major grids over all axes; inverse = 0 forward, 1 inverse
- *        normalised by 1/prod(Kd) (numpy.fft.ifftn convention), 2 inverse unnormalised.  Replaces reikna.fft.FFT
+ *        normalised by 1/prod(Kd) (numpy.fft.ifftn convention), 2 inverse unnormalised,
+ *        3 forward of a grid that is zero outside the image corner (as scale_pad leaves it; pruned
+ *        3-D plan), 4 inverse unnormalised whose result is only valid in the image corner (what
+ *        crop_scale reads; pruned 3-D plan).  Replaces reikna.fft.FFT
  *        (_nufft_class_methods_device.py:246-249, 358, 431).  cuFFT.                          */
 int b200nufft_fft(b200nufft_plan_t plan, b200_c64* grid, int nb, int inverse, void* stream);
 /* interp : y[m,c] = sum_j w[m,j] grid_c[col(m,j)].  Replaces pELL_spmv_mCoil

@@ -130,6 +130,8 @@ struct b200nufft_plan_s {
     cufftHandle fft = 0;
     int fft_nb = 0;
     bool fft_valid = false;
+    cufftHandle fft2d = 0, fft1d = 0;   // pruned 3-D transform (stages.cu)
+    bool fftp_valid = false;
     int interp_variant = 0, gridding_variant = 0;
     long long bytes = 0;
 };

@@ -393,6 +393,7 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_xin);
     cudaFree(p->d_yio);
     if (p->fft_valid) cufftDestroy(p->fft);
+    if (p->fftp_valid) { cufftDestroy(p->fft2d); cufftDestroy(p->fft1d); }
     delete p;
     return B200_OK;
 }

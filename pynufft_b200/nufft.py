@@ -217,7 +217,7 @@ class NUFFT:
         nb = self._nb_of(xx, self.ndims, 'xx')
         view, store = self._new_grid(nb, xx.dim() == self.ndims + 1)
         _lib.check(self._lib.b200nufft_scale_pad(self._plan, _ptr(xx), _ptr(store), nb, 0, 0, None, _stream()))
-        _lib.check(self._lib.b200nufft_fft(self._plan, _ptr(store), nb, 0, _stream()))
+        _lib.check(self._lib.b200nufft_fft(self._plan, _ptr(store), nb, 3, _stream()))   # zero-padded input: pruned plan
         return view
 
     def _k2y_device(self, k):

@@ -166,7 +166,7 @@ def L1TVOLS(nufft, gy, maxiter, rho):
         _lib.check(L.b200nufft_tv_rhs(nufft._plan, _ptr(AHyk), _ptr(dd), _ptr(bb), mu, LMBD, _ptr(rhs), st()))
         # xkp1 = k2xx(xx2k(rhs) / uker): zero-pad + FFT without sn scaling (:174-181)
         _lib.check(L.b200nufft_scale_pad(nufft._plan, _ptr(rhs), _ptr(k), 1, 0, 0, None, st()))
-        _lib.check(L.b200nufft_fft(nufft._plan, _ptr(k), 1, 0, st()))
+        _lib.check(L.b200nufft_fft(nufft._plan, _ptr(k), 1, 3, st()))
         _lib.check(L.b200nufft_cdiv(_ptr(k), _ptr(uker), k.numel(), st()))
         _lib.check(L.b200nufft_fft(nufft._plan, _ptr(k), 1, 1, st()))
         _lib.check(L.b200nufft_crop_scale(nufft._plan, _ptr(k), _ptr(xkp1), 1, 0, 0, None, st()))

@@ -297,3 +297,56 @@ def test_config3_properties(c3, dev):
     assert (torch.linalg.norm(f1g - f1) / torch.linalg.norm(f1)).item() < TOL
     assert (torch.linalg.norm(a1g - a1) / torch.linalg.norm(a1)).item() < TOL
     A.set_variant(0, 0)
+
+
+# ------------------------------------------------------------------------------ config 2 / 4 at full size
+def golden_angle_radial(nspokes=402, nread=512):
+    """tests/test_radial.py:10-15 of the reference: golden-angle spokes, readout r_i = pi (i - n/2)/(n/2)."""
+    s = numpy.arange(nspokes)
+    th = s * numpy.pi * (numpy.sqrt(5.0) - 1.0) / 2.0
+    r = numpy.pi * (numpy.arange(nread) - nread / 2) / (nread / 2)
+    om = numpy.stack([numpy.outer(numpy.cos(th), r), numpy.outer(numpy.sin(th), r)], -1).reshape(-1, 2)
+    return om
+
+
+@pytest.fixture(scope='module')
+def c2(dev):
+    Nd, Kd, Jd, B = (256, 256), (512, 512), (6, 6), 32
+    om = golden_angle_radial()
+    sens = coil_maps(Nd, B)
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, Jd, batch=B)
+    O.set_sense(sens)
+    A = make(dev, om, Nd, Kd, Jd, batch=B)
+    A.set_sense(sens)
+    rng = numpy.random.default_rng(4)
+    s = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    return A, O, s
+
+
+def test_config2_multicoil_radial(c2):
+    """2D 256x256, batch 32, golden-angle radial 402 spokes: forward_one2many / adjoint_many2one."""
+    A, O, s = c2
+    kindx, _, _, perm, tile, sub = A._plan_arrays()
+    assert numpy.array_equal(kindx, O.p.kindx)
+    assert numpy.array_equal(perm, orc.sort_permutation(O.p.k0, O.Kd, tile, sub))
+    y = O.forward_one2many(s).astype(numpy.complex64)
+    assert rel(A.forward_one2many(s), y) < TOL
+    assert rel(A.adjoint_many2one(y), O.adjoint_many2one(y)) < TOL
+
+
+def test_config4_solvers(c2, dev):
+    """Batched CG via selfadjoint on the config-2 geometry (10 of the 100 iterations are compared with the
+    oracle; the full 100 must stay finite) and single-coil L1TVOLS."""
+    A, O, s = c2
+    y = O.forward_one2many(s).astype(numpy.complex64)
+    x_gpu = A.solve(y, 'cg', maxiter=10)
+    assert rel(x_gpu, orc.solve_cg(O, y, 10)) < 1e-4
+    x100 = A.solve(y, 'cg', maxiter=100)
+    assert numpy.all(numpy.isfinite(x100))
+    om = golden_angle_radial()
+    A1 = make(dev, om, (256, 256), (512, 512), (6, 6))
+    O1 = orc.NUFFT()
+    O1.plan(om, (256, 256), (512, 512), (6, 6))
+    y1 = O1.forward(s).astype(numpy.complex64)
+    assert rel(A1.solve(y1, 'L1TVOLS', maxiter=5, rho=2), orc.solve_l1tvols(O1, y1, 5, 2)) < 1e-4

@@ -113,6 +113,16 @@ int b200nufft_gridding(b200nufft_plan_t plan, const b200_c64* y, b200_c64* grid,
 int b200nufft_crop_scale(b200nufft_plan_t plan, const b200_c64* grid, b200_c64* x, int nb,
                          int mode, int combine, const b200_c64* sens, void* stream);
 
+/* pad_fft : grid = FFT(zero-pad(x * [sn] * [sens])) = scale_pad followed by fft(3); ifft_crop : x =
+ *        crop(IFFT(grid)) * f [combined over coils] = fft(4) followed by crop_scale with the 1/prod(Kd)
+ *        folded in; the grid is scratch afterwards.  For Kd = 256^3 both run as three hand-written pruned
+ *        FFT passes that read/write only the image corner (csrc/fft256.cu); otherwise cuFFT.
+ *        Same reference lines as scale_pad / fft / crop_scale above.                                  */
+int b200nufft_pad_fft(b200nufft_plan_t plan, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
+                      int x_single, const b200_c64* sens, void* stream);
+int b200nufft_ifft_crop(b200nufft_plan_t plan, b200_c64* grid, b200_c64* x, int nb, int mode,
+                        int combine, const b200_c64* sens, void* stream);
+
 /* ---- compositions (plan-owned scratch grids) -------------------------------------------------
  * forward  : _forward_device  (:555-572)  x image(nb) -> y (M, nb)
  * adjoint  : _adjoint_device  (:617-633)  y (M, nb)   -> x image(nb)        (= A^H y / prod(Kd))

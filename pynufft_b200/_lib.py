@@ -29,6 +29,8 @@ SIGNATURES = {
     'b200nufft_interp': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_gridding': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_crop_scale': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'b200nufft_pad_fft': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'b200nufft_ifft_crop': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     'b200nufft_forward': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_adjoint': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_forward_one2many': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),

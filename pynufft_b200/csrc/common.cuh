@@ -132,7 +132,11 @@ struct b200nufft_plan_s {
     bool fft_valid = false;
     cufftHandle fft2d = 0, fft1d = 0;   // pruned 3-D transform (stages.cu)
     bool fftp_valid = false;
-    int interp_variant = 0, gridding_variant = 0;
+    // fused pruned FFT passes (fft256.cu)
+    float2* d_tw256 = nullptr;
+    float2* d_xc = nullptr;         // per-coil image scratch for many2one
+    int xc_nb = 0;
+    int interp_variant = 0, gridding_variant = 0, fft_variant = 0;   // 0 auto, 1 generic / cuFFT
     long long bytes = 0;
 };
 
@@ -143,6 +147,12 @@ int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int n
 int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
 bool tiled_supported(const Geom& g);
 int ensure_scratch(b200nufft_plan_t p, int nb);
+// fft256.cu
+bool fft256_supported(const Geom& g);
+int fft256_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, int apply_sn, int x_single,
+                   const float2* sens, cudaStream_t st);
+int fft256_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode, float scale, cudaStream_t st);
+int combine_coils(const float2* xc, const float2* sens, float2* s, long long N, int nb, cudaStream_t st);
 
 // ---- small device helpers ---------------------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

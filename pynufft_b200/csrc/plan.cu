@@ -389,6 +389,8 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_work);
     cudaFree(p->d_gwork);
     cudaFree(p->d_ys);
+    cudaFree(p->d_tw256);
+    cudaFree(p->d_xc);
     cudaFree(p->d_grid);
     cudaFree(p->d_xin);
     cudaFree(p->d_yio);
@@ -439,5 +441,6 @@ extern "C" int b200nufft_set_variant(b200nufft_plan_t p, int iv, int gv) {
     ARG_CHECK(iv >= 0 && iv <= 2 && gv >= 0 && gv <= 2, "variant must be 0..2");
     p->interp_variant = iv;
     p->gridding_variant = gv;
+    p->fft_variant = (iv == 1 && gv == 1) ? 1 : 0;   // 'generic' also selects the cuFFT path
     return B200_OK;
 }

@@ -216,8 +216,7 @@ class NUFFT:
         xx = self._check_dev(xx, self.Nd, 'xx')
         nb = self._nb_of(xx, self.ndims, 'xx')
         view, store = self._new_grid(nb, xx.dim() == self.ndims + 1)
-        _lib.check(self._lib.b200nufft_scale_pad(self._plan, _ptr(xx), _ptr(store), nb, 0, 0, None, _stream()))
-        _lib.check(self._lib.b200nufft_fft(self._plan, _ptr(store), nb, 3, _stream()))   # zero-padded input: pruned plan
+        _lib.check(self._lib.b200nufft_pad_fft(self._plan, _ptr(xx), _ptr(store), nb, 0, 0, None, _stream()))
         return view
 
     def _k2y_device(self, k):

@@ -116,8 +116,7 @@ def cg(nufft, gy, maxiter=30, group=None):
     # inverse FFT, crop, divide by sn  (solve_device.py:463-480)
     nb = int(xs.shape[0]) if batched else 1
     x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=nufft.device)
-    _lib.check(L.b200nufft_fft(nufft._plan, _ptr(xs), nb, 1, _stream()))
-    _lib.check(L.b200nufft_crop_scale(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
+    _lib.check(L.b200nufft_ifft_crop(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
     return x2
 
 
@@ -165,11 +164,9 @@ def L1TVOLS(nufft, gy, maxiter, rho):
     for _ in range(int(maxiter)):
         _lib.check(L.b200nufft_tv_rhs(nufft._plan, _ptr(AHyk), _ptr(dd), _ptr(bb), mu, LMBD, _ptr(rhs), st()))
         # xkp1 = k2xx(xx2k(rhs) / uker): zero-pad + FFT without sn scaling (:174-181)
-        _lib.check(L.b200nufft_scale_pad(nufft._plan, _ptr(rhs), _ptr(k), 1, 0, 0, None, st()))
-        _lib.check(L.b200nufft_fft(nufft._plan, _ptr(k), 1, 3, st()))
+        _lib.check(L.b200nufft_pad_fft(nufft._plan, _ptr(rhs), _ptr(k), 1, 0, 0, None, st()))
         _lib.check(L.b200nufft_cdiv(_ptr(k), _ptr(uker), k.numel(), st()))
-        _lib.check(L.b200nufft_fft(nufft._plan, _ptr(k), 1, 1, st()))
-        _lib.check(L.b200nufft_crop_scale(nufft._plan, _ptr(k), _ptr(xkp1), 1, 0, 0, None, st()))
+        _lib.check(L.b200nufft_ifft_crop(nufft._plan, _ptr(k), _ptr(xkp1), 1, 0, 0, None, st()))
         zf = nufft._selfadjoint_device(xkp1)
         _lib.check(L.b200nufft_tv_shrink(nufft._plan, _ptr(xkp1), _ptr(dd), _ptr(bb), LMBD, st()))
         _lib.check(L.b200nufft_tv_bregman(_ptr(AHyk), _ptr(zf), _ptr(AHy), n, st()))

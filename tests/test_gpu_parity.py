@@ -350,3 +350,29 @@ def test_config4_solvers(c2, dev):
     O1.plan(om, (256, 256), (512, 512), (6, 6))
     y1 = O1.forward(s).astype(numpy.complex64)
     assert rel(A1.solve(y1, 'L1TVOLS', maxiter=5, rho=2), orc.solve_l1tvols(O1, y1, 5, 2)) < 1e-4
+
+
+def test_fused_fft_passes_multicoil_256(dev):
+    """Kd = 256^3 takes the hand-written pruned FFT passes (csrc/fft256.cu); check them against the cuFFT +
+    generic-kernel path (variant 1) with two coils, non-cubic Nd and coil maps, and against the oracle on a
+    sample subset."""
+    Nd, Kd, Jd, B = (128, 96, 112), (256, 256, 256), (6, 6, 6), 2
+    rng = numpy.random.default_rng(9)
+    om = rng.uniform(-numpy.pi, numpy.pi, (60000, 3))
+    sens = coil_maps(Nd, B)
+    s = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    A = make(dev, om, Nd, Kd, Jd, batch=B)
+    A.set_sense(sens)
+    gs = A.to_device(s)
+    out = {}
+    for v in (1, 0):
+        A.set_variant(v, v)
+        y = A.forward_one2many(gs)
+        out[v] = (y, A.adjoint_many2one(y), A._adjoint_device(y), A._k2xx_device(A._xx2k_device(A.s2x(gs))))
+    for a, b in zip(out[0], out[1]):
+        assert (torch.linalg.norm(a - b) / torch.linalg.norm(b)).item() < TOL
+    sel = numpy.sort(rng.choice(om.shape[0], 3000, replace=False))
+    O = orc.NUFFT()
+    O.plan(om[sel], Nd, Kd, Jd, batch=B)
+    O.set_sense(sens)
+    assert rel(A.to_host(out[0][0])[sel], O.forward_one2many(s)) < TOL

@@ -49,3 +49,6 @@ algo = 8 * 256**3 + 12 * M * 18 + 8 * M
 out['interp_GBps'] = algo / out['interp_us'] / 1e3
 out['gridding_GBps'] = algo / (out['gridding_us'] - out['memset_us']) / 1e3
 print(json.dumps(out))
+k2 = torch.empty((1,) + Kd, dtype=torch.complex64, device='cuda')
+print(json.dumps({'pad_fft_us': timed(lambda: lib.b200nufft_pad_fft(A._plan, P(x.data_ptr()), P(k2.data_ptr()), 1, 1, 0, None, st())),
+                  'ifft_crop_us': timed(lambda: lib.b200nufft_ifft_crop(A._plan, P(k2.data_ptr()), P(xo.data_ptr()), 1, 1, 0, None, st()))}))

@@ -252,6 +252,8 @@ def default_tiles(Kd):
     want = 16 if nd == 3 else (32 if nd == 2 else 256)
     tile = tuple(min(want, k) for k in Kd)
     sub = tuple(8 if (nd == 3 and t % 8 == 0) else t for t in tile)
+    if nd == 2:
+        sub = (8 if tile[0] % 8 == 0 else tile[0], 16 if tile[1] % 16 == 0 else tile[1])
     return tile, sub
 
 

@@ -80,6 +80,8 @@ struct Geom {
     // cc = rel + j:  Fl[cc] = exp(+i s (cc+1)), Gl[rel] = exp(-i s rel), s = gam (N-1)/2 of the last dim
     float2 Fl[24];
     float2 Gl[16];
+    float2 F0[24];            // the same split for dimension 0 (2-D batch kernels fold both phases into the box)
+    float2 G0[16];
 };
 
 // Per-dimension float64 constants of the min-max interpolator (plan kernels only).
@@ -119,6 +121,8 @@ struct b200nufft_plan_s {
     // bin-sorted copy of the data for the tiled gridding kernel (16-byte slots)
     float4* d_ys = nullptr;
     int ys_nb = 0;
+    float2* d_ysb = nullptr;        // bin-sorted rows y[perm[i], :] for the 2-D batch kernels
+    long long ysb_elems = 0;
     // scratch grids for the compositions
     float2* d_grid = nullptr;
     int grid_nb = 0;
@@ -141,6 +145,10 @@ struct b200nufft_plan_s {
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+bool batch2d_supported(const Geom& g, int nb);
+static inline bool use_bi(const b200nufft_plan_s* p, int nb) {
+    return p->interp_variant != 1 && p->gridding_variant != 1 && batch2d_supported(p->g, nb);
+}
 
 // tiled kernels (interp_tiled.cu / grid_tiled.cu); return B200_ERR_UNSUPPORTED if geometry does not fit
 int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
@@ -153,6 +161,11 @@ int fft256_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, in
                    const float2* sens, cudaStream_t st);
 int fft256_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode, float scale, cudaStream_t st);
 int combine_coils(const float2* xc, const float2* sens, float2* s, long long N, int nb, cudaStream_t st);
+// batch2d.cu: 2-D multi-coil kernels with the coil on the lanes (grids stay coil-major)
+bool batch2d_supported(const Geom& g, int nb);
+int batch2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
+int batch2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
+
 
 // ---- small device helpers ---------------------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

@@ -182,7 +182,11 @@ static void choose_tiles(Geom& g) {
     for (int d = 0; d < g.ndim; ++d) {
         g.tile[d] = std::min(want, g.K[d]);
         g.ntile[d] = (g.K[d] + g.tile[d] - 1) / g.tile[d];
-        g.sub[d] = (g.ndim == 3 && g.tile[d] % 8 == 0) ? 8 : g.tile[d];
+        g.sub[d] = g.tile[d];
+        if (g.ndim == 3 && g.tile[d] % 8 == 0) g.sub[d] = 8;
+        // 2-D: 8 x 16 sub-tiles (13 x 21 boxes of the batch-innermost multi-coil kernels, batch2d.cu)
+        if (g.ndim == 2 && d == 0 && g.tile[d] % 8 == 0) g.sub[d] = 8;
+        if (g.ndim == 2 && d == 1 && g.tile[d] % 16 == 0) g.sub[d] = 16;
         g.nsub[d] = g.tile[d] / g.sub[d];
         g.nsubprod *= g.nsub[d];
     }
@@ -260,6 +264,10 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         double s = pc.gam[d] * ((double)g.N[d] - 1.0) / 2.0;
         for (int j = 0; j < g.J[d]; ++j)
             g.E[d][j] = make_float2((float)cos(s * (j + 1)), (float)sin(s * (j + 1)));
+        if (d == 0) {
+            for (int t = 0; t < 24; ++t) g.F0[t] = make_float2((float)cos(s * (t + 1)), (float)sin(s * (t + 1)));
+            for (int t = 0; t < 16; ++t) g.G0[t] = make_float2((float)cos(s * t), (float)-sin(s * t));
+        }
         if (d == ndim - 1) {
             for (int t = 0; t < 24; ++t) g.Fl[t] = make_float2((float)cos(s * (t + 1)), (float)sin(s * (t + 1)));
             for (int t = 0; t < 16; ++t) g.Gl[t] = make_float2((float)cos(s * t), (float)-sin(s * t));
@@ -354,7 +362,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             p->bytes += sizeof(WorkItem) * work.size();
         }
         // gridding: one item per non-empty sub-tile bin (chunks of GCHUNK), heaviest first
-        const int GCHUNK = 4096;
+        const int GCHUNK = g.ndim == 2 ? 1024 : 4096;
         std::vector<WorkItem> gwork;
         for (int b = 0; b < p->n_bins; ++b) {
             int s0 = h_bin_start[b], e = h_bin_start[b + 1];
@@ -389,6 +397,7 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_work);
     cudaFree(p->d_gwork);
     cudaFree(p->d_ys);
+    cudaFree(p->d_ysb);
     cudaFree(p->d_tw256);
     cudaFree(p->d_xc);
     cudaFree(p->d_grid);

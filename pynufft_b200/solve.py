@@ -26,16 +26,6 @@ def _stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
 
 
-def _flat(view):
-    """Underlying contiguous storage of a grid view returned by _y2k_device/_new_grid."""
-    if view.is_contiguous():
-        return view
-    nd = view.dim() - 1
-    cm = view.permute(nd, *range(nd))
-    assert cm.is_contiguous()
-    return cm
-
-
 class CudaVectorOps:
     """The fused CUDA vector kernels of csrc/solver.cu behind a tiny interface (so that the CG driver's
     control flow -- including where the all-reduces sit -- can be exercised on CPU by the tests)."""
@@ -104,17 +94,15 @@ def cg(nufft, gy, maxiter=30, group=None):
         allreduce = lambda t: dist.all_reduce(t, group=group)
     bview = nufft._y2k_device(gy)
     batched = bview.dim() == nufft.ndims + 1
-    nd = nufft.ndims
-
-    def as_view(flat):            # flat coil-major storage -> Kd(+B) view accepted by _k2y_device without a copy
-        return flat.permute(*range(1, nd + 1), 0) if batched else flat
+    nb = int(bview.shape[-1]) if batched else 1
+    store = lambda view: nufft._grid_storage(view)[0]          # contiguous storage in the library layout (no copy)
+    view = lambda flat: nufft._view_of(flat, nb, batched)
 
     def G(flat):
-        return _flat(nufft._y2k_device(nufft._k2y_device(as_view(flat))))
+        return store(nufft._y2k_device(nufft._k2y_device(view(flat))))
 
-    xs = cg_kspace(G, _flat(bview), maxiter, CudaVectorOps(L), allreduce)
+    xs = cg_kspace(G, store(bview), maxiter, CudaVectorOps(L), allreduce)
     # inverse FFT, crop, divide by sn  (solve_device.py:463-480)
-    nb = int(xs.shape[0]) if batched else 1
     x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=nufft.device)
     _lib.check(L.b200nufft_ifft_crop(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
     return x2

@@ -35,3 +35,16 @@ algo = 8 * B * 512 * 512 + 12 * om.shape[0] * 12 + 8 * B * om.shape[0]
 out['interp_GBps'] = algo / out['interp32_us'] / 1e3
 out['gridding_GBps'] = algo / out['gridding32_us'] / 1e3
 print(json.dumps(out))
+lib = A._lib; P = ctypes.c_void_p
+st = lambda: P(torch.cuda.current_stream().cuda_stream)
+x32 = A.s2x(s)
+g32 = torch.empty(Kd + (B,), dtype=torch.complex64, device='cuda')
+xo = torch.empty(Nd + (B,), dtype=torch.complex64, device='cuda')
+print(json.dumps({'layout': A._batch_inner(B),
+  'scale_pad_us': timed(lambda: lib.b200nufft_scale_pad(A._plan, P(x32.data_ptr()), P(g32.data_ptr()), B, 1, 0, None, st())),
+  'fft_us': timed(lambda: lib.b200nufft_fft(A._plan, P(g32.data_ptr()), B, 0, st())),
+  'crop_us': timed(lambda: lib.b200nufft_crop_scale(A._plan, P(g32.data_ptr()), P(xo.data_ptr()), B, 1, 0, None, st())),
+  'memset_us': timed(lambda: g32.zero_())}))
+import torch.fft
+gcm = torch.empty((B,) + Kd, dtype=torch.complex64, device='cuda')
+print(json.dumps({'torch_fft2_coil_major_us': timed(lambda: torch.fft.fft2(gcm)), 'torch_fft2_batch_inner_us': timed(lambda: torch.fft.fftn(g32, dim=(0, 1)))}))

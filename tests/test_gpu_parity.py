@@ -205,7 +205,8 @@ def coil_maps(Nd, B, seed=0):
     return maps
 
 
-@pytest.mark.parametrize('geom', [((64, 64), (128, 128), (6, 6), 8), ((16, 16, 16), (32, 32, 32), (6, 6, 6), 3)])
+@pytest.mark.parametrize('geom', [((64, 64), (128, 128), (6, 6), 8), ((16, 16, 16), (32, 32, 32), (6, 6, 6), 3),
+                                  ((40, 36), (80, 72), (6, 6), 9), ((20, 24), (40, 48), (6, 6), 40)])
 def test_multicoil(dev, geom):
     Nd, Kd, Jd, B = geom
     rng = numpy.random.default_rng(3)

@@ -48,3 +48,12 @@ print(json.dumps({'layout': A._batch_inner(B),
 import torch.fft
 gcm = torch.empty((B,) + Kd, dtype=torch.complex64, device='cuda')
 print(json.dumps({'torch_fft2_coil_major_us': timed(lambda: torch.fft.fft2(gcm)), 'torch_fft2_batch_inner_us': timed(lambda: torch.fft.fftn(g32, dim=(0, 1)))}))
+from test_gpu_parity import propeller
+om1 = propeller()
+A1 = pynufft_b200.NUFFT('cuda:0'); A1.plan(om1, Nd, Kd, Jd)
+x1 = s
+y1 = A1._forward_device(x1)
+k1 = A1._y2k_device(y1)
+print(json.dumps({'config1_M': om1.shape[0], 'c1_pair_us': timed(lambda: A1._adjoint_device(A1._forward_device(x1))),
+                  'c1_interp_us': timed(lambda: A1._k2y_device(k1)), 'c1_gridding_us': timed(lambda: A1._y2k_device(y1)),
+                  'c1_forward_us': timed(lambda: A1._forward_device(x1))}))

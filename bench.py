@@ -225,13 +225,19 @@ def run_ours(args, rank, world, local_rank):
     xa_host = torch.empty(ND, dtype=torch.complex64).pin_memory()
     xn, yn, xan = x_host.numpy(), y_host.numpy(), xa_host.numpy()
 
+    y_dev = torch.empty((M,), dtype=torch.complex64, device=dev)
+
     def e2e_step():
-        A.forward(xn, out=yn)
-        A.adjoint(yn, out=xan)
-        if dist is not None:
-            g = xa_host.to(dev, non_blocking=True)
-            dist.all_reduce(g)
-            xa_host.copy_(g)
+        A.forward(xn, out=yn)                       # H2D x, device forward, D2H y   (host API)
+        if dist is None:
+            A.adjoint(yn, out=xan)                  # H2D y, device adjoint, D2H x   (host API)
+        else:
+            # coil-sharded many2one through the host boundary: H2D y, adjoint, ONE all-reduce on the device, D2H
+            y_dev.copy_(y_host, non_blocking=True)
+            xa = A._adjoint_device(y_dev)
+            dist.all_reduce(xa)
+            xa_host.copy_(xa, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
     e2e_iters = max(3, min(args.steps, 20))
     ms_e2e = timed(e2e_step, e2e_iters, 2)
     e2e_value = world * e2e_iters / (ms_e2e * 1e-3)

@@ -27,7 +27,6 @@ constexpr int RECW2 = 20;                 // words per 2-D plan record: c0[6] c1
 constexpr int SCH = 32;                   // samples per record chunk
 constexpr int BP = 33;                    // coil pitch of a box position (complex): transposing stores stay 2-way
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ int wrap2(int i, int K) {
     i -= (i >= K) ? K : 0;
     i -= (i >= K) ? K : 0;
@@ -244,11 +243,10 @@ bool batch2d_supported(const Geom& g, int nb) {
 }
 
 int batch2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    if (!p->attr_b2d) {      // once per plan (the attribute is per device, plans are per device)
         CUDA_TRY(cudaFuncSetAttribute(k_interp2d_bi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTERP_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(k_gridding2d_bi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_SMEM));
-        configured = true;
+        p->attr_b2d = true;
     }
     if (p->n_gwork == 0) return B200_OK;
     dim3 gr(p->n_gwork, (nb + 31) / 32);
@@ -258,11 +256,10 @@ int batch2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cu
 }
 
 int batch2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    if (!p->attr_b2d) {      // once per plan (the attribute is per device, plans are per device)
         CUDA_TRY(cudaFuncSetAttribute(k_interp2d_bi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTERP_SMEM));
         CUDA_TRY(cudaFuncSetAttribute(k_gridding2d_bi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_SMEM));
-        configured = true;
+        p->attr_b2d = true;
     }
     if (p->n_gwork == 0) return B200_OK;
     if (p->ysb_elems < p->M * nb) {

@@ -140,6 +140,7 @@ struct b200nufft_plan_s {
     float2* d_tw256 = nullptr;
     float2* d_xc = nullptr;         // per-coil image scratch for many2one
     int xc_nb = 0;
+    bool attr_b2d = false, attr_grid = false, attr_interp = false;   // cudaFuncSetAttribute done on this plan's device
     int interp_variant = 0, gridding_variant = 0, fft_variant = 0;   // 0 auto, 1 generic / cuFFT
     long long bytes = 0;
 };

@@ -262,11 +262,10 @@ k_gridding_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restr
 }  // namespace
 
 int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    if (!p->attr_grid) {      // once per plan (the attribute is per device, plans are per device)
         CUDA_TRY(cudaFuncSetAttribute(k_gridding_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)GSMEM_BYTES));
-        configured = true;
+        p->attr_grid = true;
     }
     if (p->n_gwork == 0) return B200_OK;
     // sorted copy of the data (plan-owned scratch)

@@ -280,10 +280,9 @@ bool tiled_supported(const Geom& g) {
 }
 
 int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    if (!p->attr_interp) {      // once per plan (the attribute is per device, plans are per device)
         CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        configured = true;
+        p->attr_interp = true;
     }
     if (p->n_work == 0) return B200_OK;
     dim3 gr(p->n_work, nb);

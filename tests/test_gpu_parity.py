@@ -378,3 +378,22 @@ def test_fused_fft_passes_multicoil_256(dev):
     O.plan(om[sel], Nd, Kd, Jd, batch=B)
     O.set_sense(sens)
     assert rel(A.to_host(out[0][0])[sel], O.forward_one2many(s)) < TOL
+
+
+@pytest.mark.parametrize('geom', [((16, 16, 16), (32, 32, 32), (6, 6, 6), None), ((64, 64), (128, 128), (6, 6), 8)])
+def test_dense_cluster_splits_work_items(dev, geom):
+    """Thousands of samples inside one sub-tile (k-space centre of a radial scan): the bin is cut into several
+    work items / record chunks whose partial boxes must add up."""
+    Nd, Kd, Jd, B = geom
+    nd = len(Nd)
+    rng = numpy.random.default_rng(21)
+    om = numpy.concatenate([rng.uniform(-0.02, 0.02, (6000, nd)), rng.uniform(-numpy.pi, numpy.pi, (500, nd))])
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, Jd, batch=B)
+    A = make(dev, om, Nd, Kd, Jd, batch=B)
+    shp = Nd + ((B,) if B else ())
+    x = (rng.standard_normal(shp) + 1j * rng.standard_normal(shp)).astype(numpy.complex64)
+    yshape = (om.shape[0],) + ((B,) if B else ())
+    y = (rng.standard_normal(yshape) + 1j * rng.standard_normal(yshape)).astype(numpy.complex64)
+    assert rel(A.forward(x), O.forward(x)) < TOL
+    assert rel(A.adjoint(y), O.adjoint(y)) < TOL

@@ -350,9 +350,23 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
                     work.push_back(WorkItem{t, s, std::min(e, s + CHUNK), h * g.sub[0]});
             }
         }
-        std::stable_sort(work.begin(), work.end(), [](const WorkItem& a, const WorkItem& b) {
-            return (a.end - a.begin) > (b.end - b.begin);
-        });
+        // Items keep their spatial (bin) order, so that boxes whose halos overlap are processed close in time and
+        // hit in L2; only items clearly heavier than average (k-space centre of radial scans) are moved to the
+        // front, largest first.
+        auto order_items = [](std::vector<WorkItem>& v) {
+            if (v.empty()) return;
+            long long tot = 0;
+            for (const WorkItem& w : v) tot += w.end - w.begin;
+            const long long heavy = (3 * (tot / (long long)v.size() + 1)) / 2;       // 1.5 x the average item
+            // heavy items first, largest first (LPT); the rest stays in spatial order (stable)
+            std::stable_sort(v.begin(), v.end(), [heavy](const WorkItem& a, const WorkItem& b) {
+                const long long na = a.end - a.begin, nb = b.end - b.begin;
+                const bool ha = na >= heavy, hb = nb >= heavy;
+                if (ha != hb) return ha;
+                return ha && na > nb;
+            });
+        };
+        order_items(work);
         p->n_work = (int)work.size();
         if (p->n_work > 0) {
             PLAN_TRY(cudaMalloc(&p->d_work, sizeof(WorkItem) * work.size()));
@@ -368,9 +382,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             int s0 = h_bin_start[b], e = h_bin_start[b + 1];
             for (int s = s0; s < e; s += GCHUNK) gwork.push_back(WorkItem{b, s, std::min(e, s + GCHUNK), 0});
         }
-        std::stable_sort(gwork.begin(), gwork.end(), [](const WorkItem& a, const WorkItem& b) {
-            return (a.end - a.begin) > (b.end - b.begin);
-        });
+        order_items(gwork);
         p->n_gwork = (int)gwork.size();
         if (p->n_gwork > 0) {
             PLAN_TRY(cudaMalloc(&p->d_gwork, sizeof(WorkItem) * gwork.size()));

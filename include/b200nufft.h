@@ -161,6 +161,9 @@ int b200nufft_cg_init(const b200_c64* b, const b200_c64* Ax, b200_c64* r, b200_c
                       double* rsold, int64_t n, void* stream);
 /* a[i] = a[i] / b[i] (complex) -- `k /= uker`, solve_device.py:178 */
 int b200nufft_cdiv(b200_c64* a, const b200_c64* b, int64_t n, void* stream);
+/* a[i] = a[i] * b[i] (complex) -- `self.W * k` of the Toeplitz-style selfadjoint2,
+ * nufft/_nufft_class_methods_cpu.py:216-222 */
+int b200nufft_cmul(b200_c64* a, const b200_c64* b, int64_t n, void* stream);
 /* L1TVOLS, all arrays single-coil images of the plan's Nd (solve_device.py:74-275):
  *   tv_rhs    : rhs = mu*AHyk + lambda * sum_p Dt_p(d_p - b_p)           (:133-154, cDiff :936-950)
  *   tv_shrink : z_p = D_p(x); s_p = z_p + b_p; s = hypot chain + 1e-6; t = shrink(s,1/lambda)/s;

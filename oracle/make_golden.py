@@ -9,6 +9,8 @@ What is recorded per case (all produced by reference code, none by this repo):
   * helper.plan(format='pELL'): kindx, udata, meshindex, tensor_sn, alpha   (src/_helper/helper.py:620-802)
   * NUFFT() CPU operator: forward(x), adjoint(y), selfadjoint(x) and the six stages
     (nufft/_nufft_class_methods_cpu.py:168-362)
+  * selfadjoint2 (Toeplitz-style approximation, _nufft_class_methods_cpu.py:127-146) and solve(..., 'dc')
+    (linalg/solve_cpu.py:165-225)
   * the reference's *device* solvers (linalg/solve_device.py: cg, L1TVOLS) executed on a
     numpy mock of the reikna thread/program objects, so the real solver control flow is
     what pins oracle.solve_cg / oracle.solve_l1tvols.
@@ -191,6 +193,7 @@ def run_case(name, om, Nd, Kd, Jd, seed, solvers=False):
         xx=A.x2xx(x).astype(c64),
         k=A.xx2k(A.x2xx(x)).astype(c64),
         y2k=A.y2k(y_in).astype(c64),
+        selfadjoint2=A._selfadjoint2_cpu(x).astype(c64),
     )
     if solvers:
         from reference.linalg import solve_device
@@ -200,6 +203,8 @@ def run_case(name, om, Nd, Kd, Jd, seed, solvers=False):
         out['solve_y'] = y
         out['cg10'] = numpy.asarray(solve_device.solve(dev, garr(y), 'cg', maxiter=10)).astype(c64)
         out['l1tvols5'] = numpy.asarray(solve_device.solve(dev, garr(y), 'L1TVOLS', maxiter=5, rho=2)).astype(c64)
+        from reference.linalg import solve_cpu
+        out['dc2'] = numpy.asarray(solve_cpu.solve(A, y, 'dc', 2)).astype(c64)       # linalg/solve_cpu.py:165-225
     path = os.path.join(OUT, name + '.npz')
     numpy.savez_compressed(path, **out)
     print(name, 'M=%d' % M, '%.1f KB' % (os.path.getsize(path) / 1024))

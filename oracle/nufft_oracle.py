@@ -351,6 +351,14 @@ class NUFFT:
     def selfadjoint(self, x):
         return self.adjoint(self.forward(x))
 
+    def selfadjoint2(self, x):
+        """Toeplitz-style approximation of A^H A (nufft/_nufft_class_methods_cpu.py:127-146, 216-222):
+        W = |xx2k(adjoint(1_M))| once, then k2xx(W * xx2k(x)) -- no sn scaling, no interpolation."""
+        if getattr(self, 'W', None) is None:
+            W = self.xx2k(self.adjoint(numpy.ones((self.M,), dtype=numpy.complex64)))
+            self.W = (W * W.conj()) ** 0.5
+        return self.k2xx(self.W * self.xx2k(x))
+
     # --- multi-coil (linalg/nufft_hsa.py:333-388, 628-672, 723-769) ---
     def set_sense(self, coil_profile):
         if coil_profile.shape != self.Nd + (self.batch,):
@@ -411,6 +419,15 @@ def solve_cg(nufft, y, maxiter=30):
     if x2.ndim == nufft.ndims + 1:
         sn = sn[..., None]
     return (x2 / sn).astype(c64)
+
+
+def solve_dc(nufft, y, maxiter=1):
+    """'dc' (Pipe density compensation), linalg/solve_cpu.py:165-225: W = 1; W <- W / (A A^H W) `maxiter`
+    times; x = A^H (W y)."""
+    W = numpy.ones(nufft.M, dtype=numpy.complex64)
+    for _ in range(maxiter):
+        W = W / nufft.forward(nufft.adjoint(W))
+    return nufft.adjoint(W * y)
 
 
 def laplacian_kernel(Kd):

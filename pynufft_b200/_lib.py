@@ -43,6 +43,7 @@ SIGNATURES = {
     'b200nufft_cg_update_p': (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     'b200nufft_cg_init': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     'b200nufft_cdiv': (_i, [_vp, _vp, _i64, _vp]),
+    'b200nufft_cmul': (_i, [_vp, _vp, _i64, _vp]),
     'b200nufft_tv_rhs': (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp]),
     'b200nufft_tv_shrink': (_i, [_vp, _vp, _vp, _vp, _f, _vp]),
     'b200nufft_tv_bregman': (_i, [_vp, _vp, _vp, _i64, _vp]),

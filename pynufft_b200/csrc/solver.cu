@@ -123,6 +123,12 @@ __global__ void k_cdiv(float2* __restrict__ a, const float2* __restrict__ b, lon
     }
 }
 
+__global__ void k_cmul(float2* __restrict__ a, const float2* __restrict__ b, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) a[i] = cmul(a[i], b[i]);
+}
+
 // ---- L1TVOLS ---------------------------------------------------------------------------------
 // periodic neighbour along axis d of the linear image index n
 __device__ __forceinline__ long long shifted(const Geom& g, long long n, int d, int step, const int* coord,
@@ -273,6 +279,14 @@ extern "C" int b200nufft_cg_update_p(b200_c64* p, const b200_c64* r, const doubl
 extern "C" int b200nufft_cdiv(b200_c64* a, const b200_c64* b, int64_t n, void* stream) {
     ARG_CHECK(a && b && n >= 0, "cdiv: bad arguments");
     k_cdiv<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(a),
+                                                               reinterpret_cast<const float2*>(b), n);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_cmul(b200_c64* a, const b200_c64* b, int64_t n, void* stream) {
+    ARG_CHECK(a && b && n >= 0, "cmul: bad arguments");
+    k_cmul<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(a),
                                                                reinterpret_cast<const float2*>(b), n);
     LAUNCH_CHECK();
     return B200_OK;

@@ -145,6 +145,7 @@ class NUFFT:
         else:
             self.multi_Nd, self.multi_Kd, self.multi_M = Nd + (self.batch,), Kd + (self.batch,), (M, self.batch)
         self._sense = None
+        self._W = None
         return 0
 
     def release(self):
@@ -278,6 +279,23 @@ class NUFFT:
     def _selfadjoint_device(self, gx):
         return self._adjoint_device(self._forward_device(gx))
 
+    def _selfadjoint2_device(self, gx):
+        """Toeplitz-style approximation of A^H A without interpolation: k2xx(W * xx2k(x)),
+        W = |xx2k(adjoint(1_M))| computed on first use (reference: _precompute_sp_cpu / _selfadjoint2_cpu,
+        nufft/_nufft_class_methods_cpu.py:127-146, 216-222).  Single coil."""
+        self._require_plan()
+        gx = self._check_dev(gx, self.Nd, 'x')
+        if gx.dim() != self.ndims:
+            raise ValueError('selfadjoint2 is single-coil')
+        if getattr(self, '_W', None) is None:
+            ones = torch.ones((self.M,), dtype=torch.complex64, device=self.device)
+            self._W = self._xx2k_device(self._adjoint_device(ones)).abs().to(torch.complex64).contiguous()
+        k = self._xx2k_device(gx).contiguous()
+        _lib.check(self._lib.b200nufft_cmul(_ptr(k), _ptr(self._W), k.numel(), _stream()))
+        x2 = torch.empty(tuple(self.Nd), dtype=torch.complex64, device=self.device)
+        _lib.check(self._lib.b200nufft_ifft_crop(self._plan, _ptr(k), _ptr(x2), 1, 0, 0, None, _stream()))
+        return x2
+
     def _solve_device(self, gy, solver=None, *args, **kwargs):
         from .solve import solve
         return solve(self, gy, solver, *args, **kwargs)
@@ -378,6 +396,9 @@ class NUFFT:
 
     def selfadjoint(self, x):
         return self.to_host(self._selfadjoint_device(self.to_device(x)))
+
+    def selfadjoint2(self, x):
+        return self.to_host(self._selfadjoint2_device(self.to_device(x)))
 
     def solve(self, y, *args, **kwargs):
         return self.to_host(self._solve_device(self.to_device(y), *args, **kwargs))

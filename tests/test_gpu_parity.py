@@ -64,6 +64,7 @@ def test_operator_matches_reference(golden, dev, variant):
     assert rel(A.forward(x), golden['forward']) < TOL
     assert rel(A.adjoint(y), golden['adjoint']) < TOL
     assert rel(A.selfadjoint(x), golden['selfadjoint']) < TOL
+    assert rel(A.selfadjoint2(x), golden['selfadjoint2']) < TOL
     # device-array entry points (tests/test_init_device.py:70-72 of the reference call these)
     gx = A.to_device(x)
     gy = A._forward_device(gx)
@@ -81,6 +82,7 @@ def test_solvers_match_reference_device_algorithms(golden, dev):
     y = golden['solve_y']
     assert rel(A.solve(y, 'cg', maxiter=10), golden['cg10']) < 1e-4
     assert rel(A.solve(y, 'L1TVOLS', maxiter=5, rho=2), golden['l1tvols5']) < 1e-4
+    assert rel(A.solve(y, 'dc', maxiter=2), golden['dc2']) < 1e-4
 
 
 # ------------------------------------------------------------------------------ edge cases

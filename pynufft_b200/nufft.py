@@ -174,22 +174,15 @@ class NUFFT:
             raise ValueError('%s has shape %s, expected %s(+batch)' % (what, tuple(t.shape), tuple(shape_prefix)))
         return t.contiguous()
 
-    def _batch_inner(self, nb):
-        """True when a call with nb coils uses batch-innermost grids (2-D, nb >= 8), else coil-major."""
-        return False      # all grids are coil-major; the 2-D batch kernels transpose inside shared memory
-
     def _new_grid(self, nb, batched):
-        """(Kd(+ (B,)) view, contiguous storage) of a fresh grid in the layout the library uses for nb coils."""
-        if batched and self._batch_inner(nb):
-            store = torch.empty(tuple(self.Kd) + (nb,), dtype=torch.complex64, device=self.device)
-            return store, store
+        """(Kd(+ (B,)) view, contiguous coil-major storage (B, *Kd)) of a fresh grid."""
         store = torch.empty((nb,) + tuple(self.Kd), dtype=torch.complex64, device=self.device)
         if not batched:
             return store[0], store
         return store.permute(*range(1, self.ndims + 1), 0), store
 
     def _grid_storage(self, k, what='k'):
-        """Return (contiguous storage tensor in the library layout, nb, batched) for a user grid tensor."""
+        """Return (coil-major contiguous storage tensor, nb, batched) for a user grid tensor."""
         if not (isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.complex64):
             raise TypeError('%s must be a CUDA complex64 torch tensor' % what)
         if tuple(k.shape[:self.ndims]) != tuple(self.Kd):
@@ -197,14 +190,12 @@ class NUFFT:
         nb = self._nb_of(k, self.ndims, what)
         if k.dim() == self.ndims:
             return k.contiguous(), 1, False
-        if self._batch_inner(nb):
-            return k.contiguous(), nb, True
         cm = k.permute(self.ndims, *range(self.ndims))
         return cm.contiguous(), nb, True         # no copy when k is already a coil-major view
 
     def _view_of(self, store, nb, batched):
-        """Kd(+B) view of a storage tensor produced by _new_grid / _grid_storage."""
-        if not batched or self._batch_inner(nb):
+        """Kd(+B) view of a coil-major storage tensor produced by _new_grid / _grid_storage."""
+        if not batched:
             return store
         return store.permute(*range(1, self.ndims + 1), 0)
 

@@ -392,33 +392,37 @@ class NUFFT:
 # --------------------------------------------------------------------------- #
 # device solvers (linalg/solve_device.py), restated on numpy in complex64
 # --------------------------------------------------------------------------- #
-def solve_cg(nufft, y, maxiter=30):
+def solve_cg(nufft, y, maxiter=30, dtype=numpy.complex64):
     """
     linalg/solve_device.py:351-481 (batched twin linalg/solve_hsa.py:551-682):
     CG on G = interp^H interp over the oversampled grid, x0 = b, exactly `maxiter`
     steps, one alpha/beta for all coils; then k2xx and DIVIDE by sn.
+    dtype=complex64 mirrors the device arithmetic; complex128 gives the exact-arithmetic iterates (used to
+    judge how much float32 rounding the iteration amplifies on ill-conditioned trajectories).
     """
-    c64 = numpy.complex64
-    G = lambda v: nufft.y2k(nufft.k2y(v)).astype(c64)
-    b = nufft.y2k(y).astype(c64)
+    c = dtype
+    sp, spH = nufft.sp.astype(c), nufft.spH.astype(c)
+    shp = lambda v: v.reshape(nufft.Kdprod, -1) if v.ndim == nufft.ndims + 1 else v.reshape(nufft.Kdprod)
+    G = lambda v: spH.dot(sp.dot(shp(v))).reshape(v.shape).astype(c)
+    b = nufft.y2k(y).astype(c)
     x = b.copy()
-    r = (b - G(x)).astype(c64)
+    r = (b - G(x)).astype(c)
     p = r.copy()
-    rsold = c64(numpy.sum(numpy.conj(r) * r))
+    rsold = c(numpy.sum(numpy.conj(r) * r))
     for _ in range(maxiter):
         Ap = G(p)
-        alpha = c64(rsold / c64(numpy.sum(numpy.conj(p) * Ap)))
-        x = (x + alpha * p).astype(c64)
-        r = (r - alpha * Ap).astype(c64)
-        rsnew = c64(numpy.sum(numpy.conj(r) * r))
-        beta = c64(rsnew / rsold)
-        p = (r + beta * p).astype(c64)
+        alpha = c(rsold / c(numpy.sum(numpy.conj(p) * Ap)))
+        x = (x + alpha * p).astype(c)
+        r = (r - alpha * Ap).astype(c)
+        rsnew = c(numpy.sum(numpy.conj(r) * r))
+        beta = c(rsnew / rsold)
+        p = (r + beta * p).astype(c)
         rsold = rsnew
-    x2 = nufft.k2xx(x)
+    x2 = numpy.fft.ifftn(x, axes=nufft.ft_axes)[nufft._corner]
     sn = nufft.sn.real
     if x2.ndim == nufft.ndims + 1:
         sn = sn[..., None]
-    return (x2 / sn).astype(c64)
+    return (x2 / sn).astype(c)
 
 
 def solve_dc(nufft, y, maxiter=1):

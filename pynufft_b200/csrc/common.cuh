@@ -78,8 +78,8 @@ struct Geom {
     float2 E[MAXD][MAXJ];     // E_d[j] = exp(+i gam_d (N_d-1)/2 (j+1)), j = 0..J_d-1
     // last-dimension phase split used by the tiled kernels: E_last[j] = Fl[cc] * Gl[rel] with box column
     // cc = rel + j:  Fl[cc] = exp(+i s (cc+1)), Gl[rel] = exp(-i s rel), s = gam (N-1)/2 of the last dim
-    float2 Fl[24];
-    float2 Gl[16];
+    float2 Fl[40];            // 37 columns of the 2-D single-coil box
+    float2 Gl[32];
     float2 F0[24];            // the same split for dimension 0 (2-D batch kernels fold both phases into the box)
     float2 G0[16];
 };
@@ -162,6 +162,10 @@ int fft256_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, in
                    const float2* sens, cudaStream_t st);
 int fft256_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode, float scale, cudaStream_t st);
 int combine_coils(const float2* xc, const float2* sens, float2* s, long long N, int nb, cudaStream_t st);
+// single2d.cu: 2-D kernels for fewer than 8 coils
+bool single2d_supported(const Geom& g);
+int single2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
+int single2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
 // batch2d.cu: 2-D multi-coil kernels with the coil on the lanes (grids stay coil-major)
 bool batch2d_supported(const Geom& g, int nb);
 int batch2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);

@@ -107,6 +107,8 @@ extern "C" int b200nufft_interp(b200nufft_plan_t p, const b200_c64* grid, b200_c
     if (p->M == 0) return B200_OK;
     cudaStream_t st = as_stream(stream);
     if (use_bi(p, nb)) return batch2d_interp(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, st);
+    if (p->interp_variant != 1 && single2d_supported(p->g))
+        return single2d_interp(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, st);
     if (p->interp_variant != 1 && tiled_supported(p->g)) {
         return interp_tiled_launch(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, st);
     }
@@ -128,6 +130,8 @@ extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c6
     CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
     if (p->M == 0) return B200_OK;
     if (use_bi(p, nb)) return batch2d_gridding(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, st);
+    if (p->gridding_variant != 1 && single2d_supported(p->g))
+        return single2d_gridding(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, st);
     if (p->gridding_variant != 1 && tiled_supported(p->g)) {
         return gridding_tiled_launch(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, st);
     }

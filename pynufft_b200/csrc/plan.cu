@@ -269,8 +269,8 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             for (int t = 0; t < 16; ++t) g.G0[t] = make_float2((float)cos(s * t), (float)-sin(s * t));
         }
         if (d == ndim - 1) {
-            for (int t = 0; t < 24; ++t) g.Fl[t] = make_float2((float)cos(s * (t + 1)), (float)sin(s * (t + 1)));
-            for (int t = 0; t < 16; ++t) g.Gl[t] = make_float2((float)cos(s * t), (float)-sin(s * t));
+            for (int t = 0; t < 40; ++t) g.Fl[t] = make_float2((float)cos(s * (t + 1)), (float)sin(s * (t + 1)));
+            for (int t = 0; t < 32; ++t) g.Gl[t] = make_float2((float)cos(s * t), (float)-sin(s * t));
         }
     }
 
@@ -376,7 +376,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             p->bytes += sizeof(WorkItem) * work.size();
         }
         // gridding: one item per non-empty sub-tile bin (chunks of GCHUNK), heaviest first
-        const int GCHUNK = g.ndim == 2 ? 1024 : 4096;
+        const int GCHUNK = g.ndim == 2 ? 256 : 4096;      // 2-D: short serial chains per warp (dense k-space centres)
         std::vector<WorkItem> gwork;
         for (int b = 0; b < p->n_bins; ++b) {
             int s0 = h_bin_start[b], e = h_bin_start[b + 1];

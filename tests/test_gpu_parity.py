@@ -344,8 +344,12 @@ def test_config4_solvers(c2, dev):
     A, O, s = c2
     y = O.forward_one2many(s).astype(numpy.complex64)
     x_gpu = A.solve(y, 'cg', maxiter=10)
-    # 32-coil radial CG: 10 iterations amplify float32 rounding (different summation orders) to ~1e-4
-    assert rel(x_gpu, orc.solve_cg(O, y, 10)) < 3e-4
+    # The radial 32-coil system is ill-conditioned: 10 CG steps amplify float32 rounding (any change of summation
+    # order) to ~1e-4.  Judge against the exact-arithmetic (complex128) iterates of the same algorithm and allow the
+    # amplification the complex64 oracle itself shows.
+    x64 = orc.solve_cg(O, y, 10, dtype=numpy.complex128)
+    err_oracle32 = rel(orc.solve_cg(O, y, 10), x64)
+    assert rel(x_gpu, x64) < 5 * err_oracle32 + 1e-5, (rel(x_gpu, x64), err_oracle32)
     x100 = A.solve(y, 'cg', maxiter=100)
     assert numpy.all(numpy.isfinite(x100))
     om = golden_angle_radial()

@@ -40,7 +40,7 @@ st = lambda: P(torch.cuda.current_stream().cuda_stream)
 x32 = A.s2x(s)
 g32 = torch.empty(Kd + (B,), dtype=torch.complex64, device='cuda')
 xo = torch.empty(Nd + (B,), dtype=torch.complex64, device='cuda')
-print(json.dumps({'layout': A._batch_inner(B),
+print(json.dumps({
   'scale_pad_us': timed(lambda: lib.b200nufft_scale_pad(A._plan, P(x32.data_ptr()), P(g32.data_ptr()), B, 1, 0, None, st())),
   'fft_us': timed(lambda: lib.b200nufft_fft(A._plan, P(g32.data_ptr()), B, 0, st())),
   'crop_us': timed(lambda: lib.b200nufft_crop_scale(A._plan, P(g32.data_ptr()), P(xo.data_ptr()), B, 1, 0, None, st())),

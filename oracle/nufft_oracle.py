@@ -246,8 +246,17 @@ class Plan:
 # --------------------------------------------------------------------------- #
 # bin / sort permutation contract (new in the B200 build)
 # --------------------------------------------------------------------------- #
-def default_tiles(Kd):
-    """Tile / sub-tile edges the plan uses (csrc/plan.cu choose_tiles)."""
+def column_layout(Kd, Jd):
+    """True when the plan sorts by (column, first plane) (csrc/col3d.cu col3d_supported): 3-D, J = 6."""
+    return (len(Kd) == 3 and Jd is not None and tuple(Jd) == (6, 6, 6)
+            and Kd[0] >= 6 and Kd[1] >= 10 and Kd[2] >= 12 and Kd[2] % 4 == 0)
+
+
+def default_tiles(Kd, Jd=None):
+    """Tile / sub-tile edges the plan uses (csrc/plan.cu choose_tiles).  Column layout: the key
+    (column(q1, q2) * K0 + first plane) is the generic key with tile = (K0, 5, 4), sub-tile = (1, 5, 4)."""
+    if column_layout(Kd, Jd):
+        return (int(Kd[0]), 5, 4), (1, 5, 4)
     nd = len(Kd)
     want = 16 if nd == 3 else (32 if nd == 2 else 256)
     tile = tuple(min(want, k) for k in Kd)
@@ -270,7 +279,7 @@ def bin_keys(k0, Kd, tile, sub):
         ks = numpy.mod(k0[:, d] + 1, Kd[d])
         q = ks // tile[d]
         ntile = -(-Kd[d] // tile[d])
-        nsub = tile[d] // sub[d]
+        nsub = -(-tile[d] // sub[d])
         key = key * ntile + q
         skey = skey * nsub + (ks - q * tile[d]) // sub[d]
         nsubprod *= nsub

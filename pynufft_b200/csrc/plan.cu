@@ -18,6 +18,14 @@ extern "C" const char* b200nufft_last_error(void) { return g_err.c_str(); }
 extern "C" int b200nufft_version(void) { return 100; }
 extern "C" int64_t b200nufft_launch_count(void) { return g_launches.load(); }
 
+// layout preference for plans created afterwards: 1 = column sweep where supported (default), 0 = tile bins only
+static std::atomic<int> g_layout_pref{1};
+extern "C" int b200nufft_set_layout_preference(int pref) {
+    ARG_CHECK(pref == 0 || pref == 1, "layout preference must be 0 or 1");
+    g_layout_pref.store(pref);
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // float64 per-(sample, dim) math
 // ------------------------------------------------------------------------------------------
@@ -123,6 +131,59 @@ __global__ void k_build_records(Geom g, const PlanConst* __restrict__ pc,
     out[g.sumJ + 1] = (float)pi;
     reinterpret_cast<int*>(out)[g.sumJ + 2 + g.ndim] = m;
     for (int w = g.sumJ + 3 + g.ndim; w < g.recw; ++w) out[w] = 0.f;
+}
+
+// ---- column layout (col3d.cu): key = (column, first plane), 36-word records in sweep order ----
+// record words: [w9[0..8] | p0 | info | perm | P''.re P''.im | - - | c0[0..5] | 0 0 0 0 | c1[0..5] | 0 0 0 0]
+// w9[c] = c2[c - k2rel] (zero outside); info = 4 (26 - k1rel) (byte offset of c1[-k1rel]) | (p0 mod 6) << 8;
+// P'' = prod_d exp(i (om N/2 - s dk - s (k0' - 1))): the per-offset phase exp(i s (j+1)) of the reference
+// coefficient (helper.py:148-162) is carried by the modulated grid.
+__global__ void k_col_keys(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om, long long M,
+                           int nq2, int* __restrict__ keys, int* __restrict__ vals) {
+    long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    int ks[3];
+    for (int d = 0; d < 3; ++d) {
+        double q;
+        ks[d] = wrap_index(offset_k0(om[m * 3 + d], pc->gam[d], g.J[d], &q) + 1, g.K[d]);
+    }
+    keys[m] = ((ks[1] / COL_T1) * nq2 + ks[2] / COL_T2) * g.K[0] + ks[0];
+    vals[m] = (int)m;
+}
+
+__global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om,
+                              const int* __restrict__ perm, long long M, float* __restrict__ rec) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int m = perm[i];
+    float* out = rec + i * COL_RECW;
+    int* outi = reinterpret_cast<int*>(out);
+    double ph = 0.0;
+    int ks[3];
+    double c2[6];
+    for (int w = 0; w < COL_RECW; ++w) out[w] = 0.f;
+    for (int d = 0; d < 3; ++d) {
+        DimResult R;
+        const double o = om[(long long)m * 3 + d];
+        dim_math(o, d, g, pc, R);
+        ks[d] = wrap_index(R.k0 + 1, g.K[d]);
+        for (int j = 0; j < 6; ++j) {
+            if (d == 0) out[16 + j] = (float)R.c[j];
+            else if (d == 1) out[26 + j] = (float)R.c[j];
+            else c2[j] = R.c[j];
+        }
+        const double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+        ph += o * (double)g.N[d] / 2.0 - s * R.dk - s * (double)(ks[d] - 1);
+    }
+    const int k1rel = ks[1] % COL_T1, k2rel = ks[2] % COL_T2;
+    for (int j = 0; j < 6; ++j) out[k2rel + j] = (float)c2[j];
+    double sn, cs;
+    sincos(ph, &sn, &cs);
+    outi[9] = ks[0];
+    outi[10] = (4 * (26 - k1rel)) | ((ks[0] % 6) << 8);
+    outi[11] = m;
+    out[12] = (float)cs;
+    out[13] = (float)sn;
 }
 
 __global__ void k_bin_start(const int* __restrict__ sorted_keys, long long M, int nbins,
@@ -252,6 +313,14 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     p->n_tiles = 1;
     for (int d = 0; d < ndim; ++d) p->n_tiles *= g.ntile[d];
     p->n_bins = p->n_tiles * g.nsubprod;
+    {
+        const char* env = getenv("B200NUFFT_LAYOUT");
+        const bool want_col = g_layout_pref.load() == 1 && !(env && strcmp(env, "tile") == 0);
+        p->layout = (want_col && col3d_supported(g)) ? 1 : 0;
+    }
+    const int col_nq1 = (g.K[1] + COL_T1 - 1) / COL_T1, col_nq2 = g.K[2] / COL_T2;
+    const int col_ncol = col_nq1 * col_nq2;
+    if (p->layout == 1) p->n_bins = col_ncol * g.K[0];       // bins = (column, first plane)
 
     PlanConst pc;
     memset(&pc, 0, sizeof(pc));
@@ -292,10 +361,26 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     PLAN_TRY(cudaMalloc(&p->d_om, sizeof(double) * Mal * ndim));
     if (M > 0) PLAN_TRY(cudaMemcpyAsync(p->d_om, om, sizeof(double) * M * ndim, cudaMemcpyDefault, st));
     PLAN_TRY(cudaMalloc(&p->d_perm, sizeof(int) * Mal));
-    PLAN_TRY(cudaMalloc(&p->d_rec, sizeof(float) * Mal * g.recw));
+    const int recw_used = p->layout == 1 ? COL_RECW : g.recw;
+    if (p->layout == 1) {
+        PLAN_TRY(cudaMalloc(&p->d_crec, sizeof(float) * Mal * COL_RECW));
+        // modulation tables m_d[g] = exp(i s_d g), s_d = gam_d (N_d - 1) / 2
+        std::vector<float2> hm(g.K[0] + g.K[1] + g.K[2]);
+        int o = 0;
+        for (int d = 0; d < 3; ++d) {
+            const double s = pc.gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+            for (int t = 0; t < g.K[d]; ++t) hm[o + t] = make_float2((float)cos(s * t), (float)sin(s * t));
+            o += g.K[d];
+        }
+        PLAN_TRY(cudaMalloc(&p->d_mod, sizeof(float2) * hm.size()));
+        PLAN_TRY(cudaMemcpyAsync(p->d_mod, hm.data(), sizeof(float2) * hm.size(), cudaMemcpyHostToDevice, st));
+        PLAN_TRY(cudaStreamSynchronize(st));
+    } else {
+        PLAN_TRY(cudaMalloc(&p->d_rec, sizeof(float) * Mal * g.recw));
+    }
     PLAN_TRY(cudaMalloc(&p->d_bin_start, sizeof(int) * (p->n_bins + 1)));
     p->bytes = sizeof(PlanConst) + sizeof(float) * snsum + sizeof(double) * Mal * ndim +
-               sizeof(int) * Mal + sizeof(float) * Mal * g.recw + sizeof(int) * (p->n_bins + 1);
+               sizeof(int) * Mal + sizeof(float) * Mal * recw_used + sizeof(int) * (p->n_bins + 1);
 
     std::vector<int> h_bin_start(p->n_bins + 1, 0);
     if (M > 0) {
@@ -306,7 +391,10 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         PLAN_TRY(cudaMalloc(&d_vals, sizeof(int) * M));
         const int TB = 256;
         const unsigned nblk = (unsigned)((M + TB - 1) / TB);
-        k_bin_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, d_keys, d_vals);
+        if (p->layout == 1)
+            k_col_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, col_nq2, d_keys, d_vals);
+        else
+            k_bin_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, d_keys, d_vals);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         int end_bit = 1;
@@ -320,7 +408,10 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         k_bin_start<<<(p->n_bins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, p->n_bins, p->d_bin_start);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
-        k_build_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_rec);
+        if (p->layout == 1)
+            k_col_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_crec);
+        else
+            k_build_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_rec);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         PLAN_TRY(cudaMemcpyAsync(h_bin_start.data(), p->d_bin_start, sizeof(int) * (p->n_bins + 1),
@@ -335,6 +426,30 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         PLAN_TRY(cudaStreamSynchronize(st));
     }
 
+    if (p->layout == 1) {
+        // column layout: every column's samples (already in plane order) are cut into segments of at most COL_SEG
+        // samples; items stay in column order (q2 fastest), so that columns whose halos overlap run close in time
+        std::vector<WorkItem> cw;
+        const long long tail_from = M - M / 8;        // the last eighth of the samples is cut four times finer
+        for (int col = 0; col < col_ncol; ++col) {
+            const int b = h_bin_start[(size_t)col * g.K[0]], e = h_bin_start[(size_t)(col + 1) * g.K[0]];
+            const int n = e - b;
+            if (n <= 0) continue;
+            const int seg = (long long)b >= tail_from ? COL_SEG / 4 : COL_SEG;
+            const int nseg = (n + seg - 1) / seg;
+            for (int sgi = 0; sgi < nseg; ++sgi) {
+                const int sb = b + (int)((long long)n * sgi / nseg), se = b + (int)((long long)n * (sgi + 1) / nseg);
+                if (se > sb) cw.push_back(WorkItem{col, sb, se, 0});
+            }
+        }
+        p->n_cwork = (int)cw.size();
+        if (p->n_cwork > 0) {
+            PLAN_TRY(cudaMalloc(&p->d_cwork, sizeof(WorkItem) * cw.size()));
+            PLAN_TRY(cudaMemcpyAsync(p->d_cwork, cw.data(), sizeof(WorkItem) * cw.size(), cudaMemcpyHostToDevice, st));
+            PLAN_TRY(cudaStreamSynchronize(st));
+            p->bytes += sizeof(WorkItem) * cw.size();
+        }
+    } else {
     // work list for the tiled kernels: non-empty tiles, split into chunks, heaviest first
     {
         // interp: a tile is cut along dim 0 into nsub[0] slabs (sub-tiles with the same s0 are
@@ -392,6 +507,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             p->bytes += sizeof(WorkItem) * gwork.size();
         }
     }
+    }
 #undef PLAN_TRY
     *out = p;
     return B200_OK;
@@ -408,6 +524,10 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_bin_start);
     cudaFree(p->d_work);
     cudaFree(p->d_gwork);
+    cudaFree(p->d_crec);
+    cudaFree(p->d_cwork);
+    cudaFree(p->d_mod);
+    cudaFree(p->d_ccount);
     cudaFree(p->d_ys);
     cudaFree(p->d_ysb);
     cudaFree(p->d_tw256);
@@ -420,6 +540,19 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     delete p;
     return B200_OK;
 }
+
+// Standard (24-word) records for the generic kernels on a column-layout plan: built on first use.
+int ensure_std_records(b200nufft_plan_t p, cudaStream_t st) {
+    if (p->d_rec || p->M == 0) return B200_OK;
+    CUDA_TRY(cudaMalloc(&p->d_rec, sizeof(float) * p->M * p->g.recw));
+    p->bytes += sizeof(float) * p->M * p->g.recw;
+    const int TB = 256;
+    k_build_records<<<(unsigned)((p->M + TB - 1) / TB), TB, 0, st>>>(p->g, p->d_pc, p->d_om, p->d_perm, p->M, p->d_rec);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_plan_get_layout(b200nufft_plan_t p) { return p ? p->layout : -1; }
 
 static int run_export(b200nufft_plan_t p, uint32_t* kindx, float2* udata, int* k0, void* stream) {
     ARG_CHECK(p != nullptr, "plan is NULL");
@@ -449,6 +582,11 @@ extern "C" int b200nufft_plan_get_perm(b200nufft_plan_t p, int32_t* perm, void* 
 }
 extern "C" int b200nufft_plan_get_tile(b200nufft_plan_t p, int32_t* tile_host) {
     ARG_CHECK(p != nullptr, "plan is NULL");
+    if (p->layout == 1) {       // column layout: key = (q1 * nq2 + q2) * K0 + first plane
+        const int t[6] = {p->g.K[0], COL_T1, COL_T2, 1, COL_T1, COL_T2};
+        for (int i = 0; i < 6; ++i) tile_host[i] = t[i];
+        return B200_OK;
+    }
     for (int d = 0; d < p->g.ndim; ++d) {
         tile_host[d] = p->g.tile[d];
         tile_host[p->g.ndim + d] = p->g.sub[d];

@@ -47,7 +47,7 @@ def test_plan_matches_reference(golden, dev):
     assert rel(udata, golden['udata']) < 1e-6
     p = orc.Plan(golden['om'], golden['Nd'], golden['Kd'], golden['Jd'])
     assert numpy.array_equal(k0, p.k0)
-    assert (tile, sub) == orc.default_tiles(golden['Kd'])
+    assert (tile, sub) == orc.default_tiles(golden['Kd'], golden['Jd'])
     assert numpy.array_equal(perm, orc.sort_permutation(p.k0, golden['Kd'], tile, sub))   # bit-exact permutation
 
 

@@ -180,26 +180,24 @@ int b200nufft_tv_bregman(b200_c64* AHyk, const b200_c64* zf, const b200_c64* AHy
 /* ---- tuning / introspection ---------------------------------------------------------------- */
 /* kernel variant selection: interp/gridding "auto" (0), "generic" (1), "tiled" (2) */
 int b200nufft_set_variant(b200nufft_plan_t plan, int interp_variant, int gridding_variant);
-/* Sample layout of plans created afterwards: 1 (default) = column sweep where the geometry allows (3-D, Jd = 6^3,
- * Kd[2] % 8 == 0: samples sorted by (5 x 8 column of first-neighbour cells, first plane), register-resident
- * kernels of csrc/col3d.cu), 0 = tile / sub-tile bins everywhere.  plan_get_layout reports the plan's layout;
- * plan_get_tile describes its sort key either way (column layout: tile = (K0, 5, 8), sub-tile = (1, 5, 8)).     */
+/* Column-sweep gridding (csrc/col3d.cu).  Plans for 3-D, Jd = 6^3 keep, next to the tile-sorted samples, a second
+ * copy sorted by (4 x 5 column of first-neighbour cells, first plane) for the register-resident scatter kernel.
+ * set_layout_preference(0) disables it for plans created afterwards (1, the default, enables it);
+ * plan_get_layout reports 1 if the plan holds the column-sweep records.  plan_get_col_perm exports the second
+ * permutation (device pointer, M entries; may be NULL) and its sort key as (tile, sub-tile) edges of the generic
+ * bin key (host pointer, 6 entries; may be NULL): tile = (K0, 4, 5), sub-tile = (1, 4, 5).                      */
 int b200nufft_set_layout_preference(int pref);
 int b200nufft_plan_get_layout(b200nufft_plan_t plan);
-/* Native-grid variants of interp / gridding / pad_fft / ifft_crop.  The column-sweep kernels work on the
- * phase-modulated grid G'[g] = G[g] * prod_d exp(i gam_d (N_d - 1)/2 * g_d), which makes every interpolation weight
- * of the reference (helper.py:148-162, 606-618: c_j e^{i om N/2} e^{-i gam (N-1)/2 (dk - j)}) a real number times one
- * phase per sample.  forward / adjoint keep the grid in that form between the FFT passes and the sample kernels;
- * the plain stage entry points above take and return the TRUE grid (they convert, one extra pass); these variants
- * take and return the native one, for solvers that iterate on k-space vectors (linalg/solve_device.py:351-461:
- * the CG scalars are invariant under the diagonal unitary modulation).  native_is_modulated: 1 if native != true. */
-int b200nufft_native_is_modulated(b200nufft_plan_t plan);
-int b200nufft_interp_native(b200nufft_plan_t plan, const b200_c64* grid, b200_c64* y, int nb, void* stream);
-int b200nufft_gridding_native(b200nufft_plan_t plan, const b200_c64* y, b200_c64* grid, int nb, void* stream);
-int b200nufft_pad_fft_native(b200nufft_plan_t plan, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
-                             int x_single, const b200_c64* sens, void* stream);
-int b200nufft_ifft_crop_native(b200nufft_plan_t plan, b200_c64* grid, b200_c64* x, int nb, int mode, int combine,
-                               const b200_c64* sens, void* stream);
+int b200nufft_plan_get_col_perm(b200nufft_plan_t plan, int32_t* perm, int32_t* tile_host, void* stream);
+/* The column-sweep kernel produces the phase-modulated grid G'[g] = G[g] * prod_d exp(i gam_d (N_d - 1)/2 * g_d),
+ * which makes every interpolation weight of the reference (helper.py:148-162, 606-618:
+ * c_j e^{i om N/2} e^{-i gam (N-1)/2 (dk - j)}) a real number times one phase per sample.  b200nufft_gridding
+ * returns the TRUE grid (one extra pass); gridding_modulated leaves it modulated (iff gridding_is_modulated) for
+ * ifft_crop_modulated, whose inverse FFT passes undo the modulation for free.  adjoint / selfadjoint use the pair. */
+int b200nufft_gridding_is_modulated(b200nufft_plan_t plan);
+int b200nufft_gridding_modulated(b200nufft_plan_t plan, const b200_c64* y, b200_c64* grid, int nb, void* stream);
+int b200nufft_ifft_crop_modulated(b200nufft_plan_t plan, b200_c64* grid, b200_c64* x, int nb, int mode, int combine,
+                                  const b200_c64* sens, void* stream);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t b200nufft_launch_count(void);
 

@@ -246,17 +246,17 @@ class Plan:
 # --------------------------------------------------------------------------- #
 # bin / sort permutation contract (new in the B200 build)
 # --------------------------------------------------------------------------- #
-def column_layout(Kd, Jd):
-    """True when the plan sorts by (column, first plane) (csrc/col3d.cu col3d_supported): 3-D, J = 6."""
-    return (len(Kd) == 3 and Jd is not None and tuple(Jd) == (6, 6, 6)
-            and Kd[0] >= 6 and Kd[1] >= 10 and Kd[2] >= 12 and Kd[2] % 4 == 0)
+def column_sweep_tiles(Kd, Jd):
+    """(tile, sub) of the second sort the plan keeps for the column-sweep gridding kernel (csrc/col3d.cu
+    col3d_supported: 3-D, J = 6), or None.  The key (column(q1, q2) * K0 + first plane) is the generic bin key
+    with tile = (K0, 4, 5), sub-tile = (1, 4, 5)."""
+    if (len(Kd) == 3 and tuple(Jd) == (6, 6, 6) and Kd[0] >= 6 and Kd[1] >= 9 and Kd[2] >= 10):
+        return (int(Kd[0]), 4, 5), (1, 4, 5)
+    return None
 
 
-def default_tiles(Kd, Jd=None):
-    """Tile / sub-tile edges the plan uses (csrc/plan.cu choose_tiles).  Column layout: the key
-    (column(q1, q2) * K0 + first plane) is the generic key with tile = (K0, 5, 4), sub-tile = (1, 5, 4)."""
-    if column_layout(Kd, Jd):
-        return (int(Kd[0]), 5, 4), (1, 5, 4)
+def default_tiles(Kd):
+    """Tile / sub-tile edges the plan uses (csrc/plan.cu choose_tiles)."""
     nd = len(Kd)
     want = 16 if nd == 3 else (32 if nd == 2 else 256)
     tile = tuple(min(want, k) for k in Kd)

@@ -50,11 +50,10 @@ SIGNATURES = {
     'b200nufft_set_variant': (_i, [_vp, _i, _i]),
     'b200nufft_set_layout_preference': (_i, [_i]),
     'b200nufft_plan_get_layout': (_i, [_vp]),
-    'b200nufft_native_is_modulated': (_i, [_vp]),
-    'b200nufft_interp_native': (_i, [_vp, _vp, _vp, _i, _vp]),
-    'b200nufft_gridding_native': (_i, [_vp, _vp, _vp, _i, _vp]),
-    'b200nufft_pad_fft_native': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    'b200nufft_ifft_crop_native': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'b200nufft_plan_get_col_perm': (_i, [_vp, _vp, _vp, _vp]),
+    'b200nufft_gridding_is_modulated': (_i, [_vp]),
+    'b200nufft_gridding_modulated': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'b200nufft_ifft_crop_modulated': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     'b200nufft_launch_count': (_i64, []),
 }
 

@@ -93,8 +93,9 @@ struct PlanConst {
     double T[MAXD][MAXJ * MAXJ];// T_d row-major J x J (helper.py:1060-1083)
 };
 
-// column layout (col3d.cu): 5 x 4 cross-section columns swept along dim 0; 36-word sample records
-constexpr int COL_T1 = 5, COL_T2 = 4, COL_RECW = 36, COL_SEG = 320;
+// column-sweep gridding (col3d.cu): 4 x 5 cross-section columns of first-neighbour cells swept along dim 0;
+// 32-word sample records in sweep order
+constexpr int COL_T1 = 4, COL_T2 = 5, COL_RECW = 32, COL_SEG = 320;
 
 struct WorkItem {   // one launch unit of the tiled kernels: samples [begin, end) of one tile
     int tile;
@@ -121,9 +122,11 @@ struct b200nufft_plan_s {
     int n_gwork = 0;
     int n_tiles = 0;
     int n_bins = 0;
-    // column layout (3-D, J = 6; col3d.cu): samples sorted by (column, first plane)
-    int layout = 0;                 // 0 = tile / sub-tile bins, 1 = column sweep
+    // column-sweep gridding (3-D, J = 6; col3d.cu): a second copy of the samples sorted by (column, first plane)
+    bool has_col = false;
+    int* d_cperm = nullptr;         // (M,) sweep-order permutation (parity export)
     float* d_crec = nullptr;        // (M, COL_RECW) records in sweep order
+    float4* d_cside = nullptr;      // (M,) (P''.re, P''.im, original index, 0) in sweep order
     WorkItem* d_cwork = nullptr;    // (column, begin, end) segments of at most COL_SEG samples
     int n_cwork = 0;
     int* d_ccount = nullptr;        // per-coil work counters of the persistent column kernels
@@ -168,23 +171,19 @@ int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int n
 int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
 bool tiled_supported(const Geom& g);
 int ensure_scratch(b200nufft_plan_t p, int nb);
-// col3d.cu: register-resident column-sweep kernels (3-D, J = 6) on the phase-modulated grid
+// col3d.cu: register-resident column-sweep gridding (3-D, J = 6); the grid it produces is phase-modulated
 bool col3d_supported(const Geom& g);
-int col3d_interp(b200nufft_plan_t p, const float2* grid_mod, float2* y, int nb, cudaStream_t st);
 int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st);
-int col3d_modulate(b200nufft_plan_t p, const float2* in, float2* out, int nb, int conj_, cudaStream_t st);
-int ensure_std_records(b200nufft_plan_t p, cudaStream_t st);
-// the plan's native grid is phase-modulated iff both operators run on the column-sweep kernels
-static inline bool native_modulated(const b200nufft_plan_s* p) {
-    return p->layout == 1 && p->interp_variant != 1 && p->gridding_variant != 1;
-}
-// interp / gridding with the grid in native form (native = true) or as the true grid (native = false)
-int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool native);
-int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool native);
-// fft256.cu; `modulated`: the grid leaves / enters phase-modulated (col3d.cu)
+int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st);
+// the gridding output is phase-modulated iff the column-sweep kernel runs (gridding variant "auto")
+static inline bool gridding_modulated(const b200nufft_plan_s* p) { return p->has_col && p->gridding_variant == 0; }
+int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
+// modulated_ok: the caller accepts the phase-modulated grid (it hands it to ifft_crop_impl(..., modulated))
+int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool modulated_ok);
+// fft256.cu; `modulated`: the grid enters phase-modulated (col3d.cu)
 bool fft256_supported(const Geom& g);
 int fft256_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, int apply_sn, int x_single,
-                   const float2* sens, bool modulated, cudaStream_t st);
+                   const float2* sens, cudaStream_t st);
 int fft256_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode, float scale, bool modulated,
                    cudaStream_t st);
 int combine_coils(const float2* xc, const float2* sens, float2* s, long long N, int nb, cudaStream_t st);

@@ -101,29 +101,14 @@ k_gridding_generic(Geom g, const float* __restrict__ rec, long long M, const flo
     }
 }
 
-int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool native) {
+int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
     if (p->M == 0) return B200_OK;
-    if (p->layout == 1) {
-        if (p->interp_variant != 1) {
-            if (!(native && native_modulated(p))) {      // true grid in: modulate a copy
-                int rc = ensure_scratch(p, nb);
-                if (rc) return rc;
-                rc = col3d_modulate(p, grid, p->d_grid, nb, 0, st);
-                if (rc) return rc;
-                grid = p->d_grid;
-            }
-            return col3d_interp(p, grid, y, nb, st);
-        }
-        int rc = ensure_std_records(p, st);
-        if (rc) return rc;
-    } else {
-        if (use_bi(p, nb)) return batch2d_interp(p, grid, y, nb, st);
-        if (p->interp_variant != 1 && single2d_supported(p->g)) return single2d_interp(p, grid, y, nb, st);
-        if (p->interp_variant != 1 && tiled_supported(p->g)) return interp_tiled_launch(p, grid, y, nb, st);
-        if (p->interp_variant == 2) {
-            b200_set_error("interp: tiled variant requested but geometry unsupported");
-            return B200_ERR_UNSUPPORTED;
-        }
+    if (use_bi(p, nb)) return batch2d_interp(p, grid, y, nb, st);
+    if (p->interp_variant != 1 && single2d_supported(p->g)) return single2d_interp(p, grid, y, nb, st);
+    if (p->interp_variant != 1 && tiled_supported(p->g)) return interp_tiled_launch(p, grid, y, nb, st);
+    if (p->interp_variant == 2) {
+        b200_set_error("interp: tiled variant requested but geometry unsupported");
+        return B200_ERR_UNSUPPORTED;
     }
     dim3 gr((unsigned)((p->M + GEN_WARPS - 1) / GEN_WARPS), nb);
     k_interp_generic<<<gr, GEN_WARPS * 32, 0, st>>>(p->g, p->d_rec, p->M, grid, y, nb);
@@ -131,26 +116,22 @@ int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaS
     return B200_OK;
 }
 
-int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool native) {
+// modulated_ok: the caller takes the grid phase-modulated when the column-sweep kernel ran (gridding_modulated(p));
+// otherwise the true grid is returned (one extra pass after the column-sweep kernel).
+int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool modulated_ok) {
     CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
     if (p->M == 0) return B200_OK;
-    if (p->layout == 1) {
-        if (p->gridding_variant != 1) {
-            int rc = col3d_gridding(p, y, grid, nb, st);
-            if (rc) return rc;
-            if (!(native && native_modulated(p))) return col3d_modulate(p, grid, grid, nb, 1, st);   // true grid out
-            return B200_OK;
-        }
-        int rc = ensure_std_records(p, st);
-        if (rc) return rc;
-    } else {
-        if (use_bi(p, nb)) return batch2d_gridding(p, y, grid, nb, st);
-        if (p->gridding_variant != 1 && single2d_supported(p->g)) return single2d_gridding(p, y, grid, nb, st);
-        if (p->gridding_variant != 1 && tiled_supported(p->g)) return gridding_tiled_launch(p, y, grid, nb, st);
-        if (p->gridding_variant == 2) {
-            b200_set_error("gridding: tiled variant requested but geometry unsupported");
-            return B200_ERR_UNSUPPORTED;
-        }
+    if (gridding_modulated(p)) {
+        int rc = col3d_gridding(p, y, grid, nb, st);
+        if (rc || modulated_ok) return rc;
+        return col3d_demodulate(p, grid, nb, st);
+    }
+    if (use_bi(p, nb)) return batch2d_gridding(p, y, grid, nb, st);
+    if (p->gridding_variant != 1 && single2d_supported(p->g)) return single2d_gridding(p, y, grid, nb, st);
+    if (p->gridding_variant != 1 && tiled_supported(p->g)) return gridding_tiled_launch(p, y, grid, nb, st);
+    if (p->gridding_variant == 2) {
+        b200_set_error("gridding: tiled variant requested but geometry unsupported");
+        return B200_ERR_UNSUPPORTED;
     }
     dim3 gr((unsigned)((p->M + GEN_WARPS - 1) / GEN_WARPS), nb);
     k_gridding_generic<<<gr, GEN_WARPS * 32, 0, st>>>(p->g, p->d_rec, p->M, y, grid, nb);
@@ -161,7 +142,7 @@ int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cud
 extern "C" int b200nufft_interp(b200nufft_plan_t p, const b200_c64* grid, b200_c64* y, int nb, void* stream) {
     ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "interp: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
-    return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream), false);
+    return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream));
 }
 
 extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {
@@ -170,14 +151,9 @@ extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c6
     return gridding_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, as_stream(stream), false);
 }
 
-// native-grid variants: the grid is in the plan's native form (b200nufft_native_is_modulated)
-extern "C" int b200nufft_interp_native(b200nufft_plan_t p, const b200_c64* grid, b200_c64* y, int nb, void* stream) {
-    ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "interp: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
-    return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream), true);
-}
-
-extern "C" int b200nufft_gridding_native(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {
+// gridding that leaves the grid in the form b200nufft_ifft_crop_modulated takes (phase-modulated when
+// b200nufft_gridding_is_modulated(plan), the true grid otherwise)
+extern "C" int b200nufft_gridding_modulated(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {
     ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "gridding: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
     return gridding_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, as_stream(stream), true);

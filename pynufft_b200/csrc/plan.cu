@@ -18,7 +18,8 @@ extern "C" const char* b200nufft_last_error(void) { return g_err.c_str(); }
 extern "C" int b200nufft_version(void) { return 100; }
 extern "C" int64_t b200nufft_launch_count(void) { return g_launches.load(); }
 
-// layout preference for plans created afterwards: 1 = column sweep where supported (default), 0 = tile bins only
+// preference for plans created afterwards: 1 = also build the column-sweep gridding records where supported
+// (default), 0 = tile bins only
 static std::atomic<int> g_layout_pref{1};
 extern "C" int b200nufft_set_layout_preference(int pref) {
     ARG_CHECK(pref == 0 || pref == 1, "layout preference must be 0 or 1");
@@ -133,11 +134,14 @@ __global__ void k_build_records(Geom g, const PlanConst* __restrict__ pc,
     for (int w = g.sumJ + 3 + g.ndim; w < g.recw; ++w) out[w] = 0.f;
 }
 
-// ---- column layout (col3d.cu): key = (column, first plane), 36-word records in sweep order ----
-// record words: [w9[0..8] | p0 | info | perm | P''.re P''.im | - - | c0[0..5] | 0 0 0 0 | c1[0..5] | 0 0 0 0]
-// w9[c] = c2[c - k2rel] (zero outside); info = 4 (26 - k1rel) (byte offset of c1[-k1rel]) | (p0 mod 6) << 8;
-// P'' = prod_d exp(i (om N/2 - s dk - s (k0' - 1))): the per-offset phase exp(i s (j+1)) of the reference
-// coefficient (helper.py:148-162) is carried by the modulated grid.
+// ---- column-sweep gridding (col3d.cu): key = (column, first plane), 32-word records in sweep order ----
+// A column is a COL_T1 x COL_T2 cross-section (dims 1, 2) of first-neighbour cells; its box is 9 rows x 10 columns.
+// record words: [c1g[0..11] | c0rot[0..5] | p0 | p0 mod 6 | w10[0..9] | 0 0]
+//   c1g[4 g + i] = c1t[g + 3 i] (g, i = 0..2), c1t[b] = c1[b - k1rel] (zero outside the footprint): box rows g, g+3, g+6
+//   c0rot[(p0 + j) mod 6] = c0[j]: weight of the plane slot that holds plane p0 + j
+//   w10[c] = c2[c - k2rel] (zero outside the footprint): box columns
+// side: (P''.re, P''.im, original index, 0), P'' = prod_d exp(i (om N/2 - s dk - s (k0' - 1))): the per-offset phase
+// exp(i s (j+1)) of the reference coefficient (helper.py:148-162) is carried by the modulated grid.
 __global__ void k_col_keys(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om, long long M,
                            int nq2, int* __restrict__ keys, int* __restrict__ vals) {
     long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -152,7 +156,8 @@ __global__ void k_col_keys(Geom g, const PlanConst* __restrict__ pc, const doubl
 }
 
 __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om,
-                              const int* __restrict__ perm, long long M, float* __restrict__ rec) {
+                              const int* __restrict__ perm, long long M, float* __restrict__ rec,
+                              float4* __restrict__ side) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= M) return;
     const int m = perm[i];
@@ -160,30 +165,33 @@ __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const do
     int* outi = reinterpret_cast<int*>(out);
     double ph = 0.0;
     int ks[3];
-    double c2[6];
     for (int w = 0; w < COL_RECW; ++w) out[w] = 0.f;
     for (int d = 0; d < 3; ++d) {
         DimResult R;
         const double o = om[(long long)m * 3 + d];
         dim_math(o, d, g, pc, R);
-        ks[d] = wrap_index(R.k0 + 1, g.K[d]);
+        const int k = wrap_index(R.k0 + 1, g.K[d]);
+        ks[d] = k;
         for (int j = 0; j < 6; ++j) {
-            if (d == 0) out[16 + j] = (float)R.c[j];
-            else if (d == 1) out[26 + j] = (float)R.c[j];
-            else c2[j] = R.c[j];
+            const float cj = (float)R.c[j];
+            if (d == 0) {
+                out[12 + (k + j) % 6] = cj;            // slot of plane k + j
+            } else if (d == 1) {
+                const int b = k % COL_T1 + j;          // box row 0..8
+                out[4 * (b % 3) + b / 3] = cj;
+            } else {
+                out[20 + k % COL_T2 + j] = cj;         // box column 0..9
+            }
         }
         const double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
-        ph += o * (double)g.N[d] / 2.0 - s * R.dk - s * (double)(ks[d] - 1);
+        ph += o * (double)g.N[d] / 2.0 - s * R.dk - s * (double)(k - 1);
     }
-    const int k1rel = ks[1] % COL_T1, k2rel = ks[2] % COL_T2;
-    for (int j = 0; j < 6; ++j) out[k2rel + j] = (float)c2[j];
+    const int s0 = ks[0] % 6;
+    outi[18] = ks[0];
+    outi[19] = s0;
     double sn, cs;
     sincos(ph, &sn, &cs);
-    outi[9] = ks[0];
-    outi[10] = (4 * (26 - k1rel)) | ((ks[0] % 6) << 8);
-    outi[11] = m;
-    out[12] = (float)cs;
-    out[13] = (float)sn;
+    side[i] = make_float4((float)cs, (float)sn, __int_as_float(m), 0.f);
 }
 
 __global__ void k_bin_start(const int* __restrict__ sorted_keys, long long M, int nbins,
@@ -316,11 +324,8 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     {
         const char* env = getenv("B200NUFFT_LAYOUT");
         const bool want_col = g_layout_pref.load() == 1 && !(env && strcmp(env, "tile") == 0);
-        p->layout = (want_col && col3d_supported(g)) ? 1 : 0;
+        p->has_col = want_col && col3d_supported(g);
     }
-    const int col_nq1 = (g.K[1] + COL_T1 - 1) / COL_T1, col_nq2 = g.K[2] / COL_T2;
-    const int col_ncol = col_nq1 * col_nq2;
-    if (p->layout == 1) p->n_bins = col_ncol * g.K[0];       // bins = (column, first plane)
 
     PlanConst pc;
     memset(&pc, 0, sizeof(pc));
@@ -361,26 +366,10 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     PLAN_TRY(cudaMalloc(&p->d_om, sizeof(double) * Mal * ndim));
     if (M > 0) PLAN_TRY(cudaMemcpyAsync(p->d_om, om, sizeof(double) * M * ndim, cudaMemcpyDefault, st));
     PLAN_TRY(cudaMalloc(&p->d_perm, sizeof(int) * Mal));
-    const int recw_used = p->layout == 1 ? COL_RECW : g.recw;
-    if (p->layout == 1) {
-        PLAN_TRY(cudaMalloc(&p->d_crec, sizeof(float) * Mal * COL_RECW));
-        // modulation tables m_d[g] = exp(i s_d g), s_d = gam_d (N_d - 1) / 2
-        std::vector<float2> hm(g.K[0] + g.K[1] + g.K[2]);
-        int o = 0;
-        for (int d = 0; d < 3; ++d) {
-            const double s = pc.gam[d] * ((double)g.N[d] - 1.0) / 2.0;
-            for (int t = 0; t < g.K[d]; ++t) hm[o + t] = make_float2((float)cos(s * t), (float)sin(s * t));
-            o += g.K[d];
-        }
-        PLAN_TRY(cudaMalloc(&p->d_mod, sizeof(float2) * hm.size()));
-        PLAN_TRY(cudaMemcpyAsync(p->d_mod, hm.data(), sizeof(float2) * hm.size(), cudaMemcpyHostToDevice, st));
-        PLAN_TRY(cudaStreamSynchronize(st));
-    } else {
-        PLAN_TRY(cudaMalloc(&p->d_rec, sizeof(float) * Mal * g.recw));
-    }
+    PLAN_TRY(cudaMalloc(&p->d_rec, sizeof(float) * Mal * g.recw));
     PLAN_TRY(cudaMalloc(&p->d_bin_start, sizeof(int) * (p->n_bins + 1)));
     p->bytes = sizeof(PlanConst) + sizeof(float) * snsum + sizeof(double) * Mal * ndim +
-               sizeof(int) * Mal + sizeof(float) * Mal * recw_used + sizeof(int) * (p->n_bins + 1);
+               sizeof(int) * Mal + sizeof(float) * Mal * g.recw + sizeof(int) * (p->n_bins + 1);
 
     std::vector<int> h_bin_start(p->n_bins + 1, 0);
     if (M > 0) {
@@ -391,10 +380,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         PLAN_TRY(cudaMalloc(&d_vals, sizeof(int) * M));
         const int TB = 256;
         const unsigned nblk = (unsigned)((M + TB - 1) / TB);
-        if (p->layout == 1)
-            k_col_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, col_nq2, d_keys, d_vals);
-        else
-            k_bin_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, d_keys, d_vals);
+        k_bin_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, d_keys, d_vals);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         int end_bit = 1;
@@ -408,10 +394,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         k_bin_start<<<(p->n_bins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, p->n_bins, p->d_bin_start);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
-        if (p->layout == 1)
-            k_col_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_crec);
-        else
-            k_build_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_rec);
+        k_build_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_rec);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         PLAN_TRY(cudaMemcpyAsync(h_bin_start.data(), p->d_bin_start, sizeof(int) * (p->n_bins + 1),
@@ -426,30 +409,6 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         PLAN_TRY(cudaStreamSynchronize(st));
     }
 
-    if (p->layout == 1) {
-        // column layout: every column's samples (already in plane order) are cut into segments of at most COL_SEG
-        // samples; items stay in column order (q2 fastest), so that columns whose halos overlap run close in time
-        std::vector<WorkItem> cw;
-        const long long tail_from = M - M / 8;        // the last eighth of the samples is cut four times finer
-        for (int col = 0; col < col_ncol; ++col) {
-            const int b = h_bin_start[(size_t)col * g.K[0]], e = h_bin_start[(size_t)(col + 1) * g.K[0]];
-            const int n = e - b;
-            if (n <= 0) continue;
-            const int seg = (long long)b >= tail_from ? COL_SEG / 4 : COL_SEG;
-            const int nseg = (n + seg - 1) / seg;
-            for (int sgi = 0; sgi < nseg; ++sgi) {
-                const int sb = b + (int)((long long)n * sgi / nseg), se = b + (int)((long long)n * (sgi + 1) / nseg);
-                if (se > sb) cw.push_back(WorkItem{col, sb, se, 0});
-            }
-        }
-        p->n_cwork = (int)cw.size();
-        if (p->n_cwork > 0) {
-            PLAN_TRY(cudaMalloc(&p->d_cwork, sizeof(WorkItem) * cw.size()));
-            PLAN_TRY(cudaMemcpyAsync(p->d_cwork, cw.data(), sizeof(WorkItem) * cw.size(), cudaMemcpyHostToDevice, st));
-            PLAN_TRY(cudaStreamSynchronize(st));
-            p->bytes += sizeof(WorkItem) * cw.size();
-        }
-    } else {
     // work list for the tiled kernels: non-empty tiles, split into chunks, heaviest first
     {
         // interp: a tile is cut along dim 0 into nsub[0] slabs (sub-tiles with the same s0 are
@@ -507,6 +466,83 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             p->bytes += sizeof(WorkItem) * gwork.size();
         }
     }
+
+    // ---- column-sweep gridding: second sort by (column, first plane), records, work items ----
+    if (p->has_col && M > 0) {
+        const int col_nq1 = (g.K[1] + COL_T1 - 1) / COL_T1, col_nq2 = (g.K[2] + COL_T2 - 1) / COL_T2;
+        const int col_ncol = col_nq1 * col_nq2;
+        const int n_cbins = col_ncol * g.K[0];               // bins = (column, first plane)
+        PLAN_TRY(cudaMalloc(&p->d_cperm, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&p->d_crec, sizeof(float) * M * COL_RECW));
+        PLAN_TRY(cudaMalloc(&p->d_cside, sizeof(float4) * M));
+        p->bytes += sizeof(int) * M + sizeof(float) * M * COL_RECW + sizeof(float4) * M;
+        {   // modulation tables m_d[g] = exp(i s_d g), s_d = gam_d (N_d - 1) / 2
+            std::vector<float2> hm(g.K[0] + g.K[1] + g.K[2]);
+            int o = 0;
+            for (int d = 0; d < 3; ++d) {
+                const double sd = pc.gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+                for (int t = 0; t < g.K[d]; ++t) hm[o + t] = make_float2((float)cos(sd * t), (float)sin(sd * t));
+                o += g.K[d];
+            }
+            PLAN_TRY(cudaMalloc(&p->d_mod, sizeof(float2) * hm.size()));
+            PLAN_TRY(cudaMemcpyAsync(p->d_mod, hm.data(), sizeof(float2) * hm.size(), cudaMemcpyHostToDevice, st));
+            PLAN_TRY(cudaStreamSynchronize(st));
+        }
+        int *d_keys = nullptr, *d_keys_s = nullptr, *d_vals = nullptr, *d_cbin = nullptr;
+        void* d_tmp = nullptr;
+        PLAN_TRY(cudaMalloc(&d_keys, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&d_keys_s, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&d_vals, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&d_cbin, sizeof(int) * (n_cbins + 1)));
+        const int TB = 256;
+        const unsigned nblk = (unsigned)((M + TB - 1) / TB);
+        k_col_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, col_nq2, d_keys, d_vals);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        int end_bit = 1;
+        while ((1LL << end_bit) < n_cbins) ++end_bit;
+        size_t tmp_bytes = 0;
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_cperm, (int)M, 0,
+                                                 end_bit, st));
+        PLAN_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_cperm, (int)M, 0,
+                                                 end_bit, st));
+        k_bin_start<<<(n_cbins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, n_cbins, d_cbin);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        k_col_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_cperm, M, p->d_crec, p->d_cside);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        std::vector<int> h_cbin(n_cbins + 1, 0);
+        PLAN_TRY(cudaMemcpyAsync(h_cbin.data(), d_cbin, sizeof(int) * (n_cbins + 1), cudaMemcpyDeviceToHost, st));
+        PLAN_TRY(cudaStreamSynchronize(st));
+        cudaFree(d_keys);
+        cudaFree(d_keys_s);
+        cudaFree(d_vals);
+        cudaFree(d_cbin);
+        cudaFree(d_tmp);
+        // every column's samples (already in plane order) are cut into segments of at most COL_SEG samples; items
+        // stay in column order (q2 fastest), so that columns whose halos overlap run close in time
+        std::vector<WorkItem> cw;
+        const long long tail_from = M - M / 8;        // the last eighth of the samples is cut four times finer
+        for (int col = 0; col < col_ncol; ++col) {
+            const int b = h_cbin[(size_t)col * g.K[0]], e = h_cbin[(size_t)(col + 1) * g.K[0]];
+            const int n = e - b;
+            if (n <= 0) continue;
+            const int seg = (long long)b >= tail_from ? COL_SEG / 4 : COL_SEG;
+            const int nseg = (n + seg - 1) / seg;
+            for (int sgi = 0; sgi < nseg; ++sgi) {
+                const int sb = b + (int)((long long)n * sgi / nseg), se = b + (int)((long long)n * (sgi + 1) / nseg);
+                if (se > sb) cw.push_back(WorkItem{col, sb, se, 0});
+            }
+        }
+        p->n_cwork = (int)cw.size();
+        PLAN_TRY(cudaMalloc(&p->d_cwork, sizeof(WorkItem) * cw.size()));
+        PLAN_TRY(cudaMemcpyAsync(p->d_cwork, cw.data(), sizeof(WorkItem) * cw.size(), cudaMemcpyHostToDevice, st));
+        PLAN_TRY(cudaStreamSynchronize(st));
+        p->bytes += sizeof(WorkItem) * cw.size();
+    } else {
+        p->has_col = false;
     }
 #undef PLAN_TRY
     *out = p;
@@ -524,7 +560,9 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_bin_start);
     cudaFree(p->d_work);
     cudaFree(p->d_gwork);
+    cudaFree(p->d_cperm);
     cudaFree(p->d_crec);
+    cudaFree(p->d_cside);
     cudaFree(p->d_cwork);
     cudaFree(p->d_mod);
     cudaFree(p->d_ccount);
@@ -541,18 +579,7 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     return B200_OK;
 }
 
-// Standard (24-word) records for the generic kernels on a column-layout plan: built on first use.
-int ensure_std_records(b200nufft_plan_t p, cudaStream_t st) {
-    if (p->d_rec || p->M == 0) return B200_OK;
-    CUDA_TRY(cudaMalloc(&p->d_rec, sizeof(float) * p->M * p->g.recw));
-    p->bytes += sizeof(float) * p->M * p->g.recw;
-    const int TB = 256;
-    k_build_records<<<(unsigned)((p->M + TB - 1) / TB), TB, 0, st>>>(p->g, p->d_pc, p->d_om, p->d_perm, p->M, p->d_rec);
-    LAUNCH_CHECK();
-    return B200_OK;
-}
-
-extern "C" int b200nufft_plan_get_layout(b200nufft_plan_t p) { return p ? p->layout : -1; }
+extern "C" int b200nufft_plan_get_layout(b200nufft_plan_t p) { return p ? (p->has_col ? 1 : 0) : -1; }
 
 static int run_export(b200nufft_plan_t p, uint32_t* kindx, float2* udata, int* k0, void* stream) {
     ARG_CHECK(p != nullptr, "plan is NULL");
@@ -582,15 +609,23 @@ extern "C" int b200nufft_plan_get_perm(b200nufft_plan_t p, int32_t* perm, void* 
 }
 extern "C" int b200nufft_plan_get_tile(b200nufft_plan_t p, int32_t* tile_host) {
     ARG_CHECK(p != nullptr, "plan is NULL");
-    if (p->layout == 1) {       // column layout: key = (q1 * nq2 + q2) * K0 + first plane
-        const int t[6] = {p->g.K[0], COL_T1, COL_T2, 1, COL_T1, COL_T2};
-        for (int i = 0; i < 6; ++i) tile_host[i] = t[i];
-        return B200_OK;
-    }
     for (int d = 0; d < p->g.ndim; ++d) {
         tile_host[d] = p->g.tile[d];
         tile_host[p->g.ndim + d] = p->g.sub[d];
     }
+    return B200_OK;
+}
+// sweep-order permutation of the column-sweep gridding records: stable argsort of
+// key = (q1 * nq2 + q2) * K0 + first plane, i.e. the generic bin key with tile = (K0, T1, T2), sub-tile = (1, T1, T2)
+extern "C" int b200nufft_plan_get_col_perm(b200nufft_plan_t p, int32_t* perm, int32_t* tile_host, void* stream) {
+    ARG_CHECK(p != nullptr, "plan is NULL");
+    ARG_CHECK(p->has_col, "plan has no column-sweep records");
+    if (tile_host) {
+        const int t[6] = {p->g.K[0], COL_T1, COL_T2, 1, COL_T1, COL_T2};
+        for (int i = 0; i < 6; ++i) tile_host[i] = t[i];
+    }
+    if (perm && p->M > 0)
+        CUDA_TRY(cudaMemcpyAsync(perm, p->d_cperm, sizeof(int) * p->M, cudaMemcpyDeviceToDevice, as_stream(stream)));
     return B200_OK;
 }
 extern "C" int64_t b200nufft_plan_bytes(b200nufft_plan_t p) { return p ? p->bytes : 0; }

@@ -293,38 +293,29 @@ int ensure_scratch(b200nufft_plan_t p, int nb) {
 
 // pad_fft: grid = FFT(zero-pad(x * [sn] * [sens])).  Fused pruned passes when the geometry allows
 // (fft256.cu), else scale_pad + cuFFT (pruned plan for other 3-D sizes).
-// `native`: the grid leaves in the plan's native form (phase-modulated when the column-sweep kernels are in use,
-// col3d.cu; identical to the true grid otherwise).
-static int pad_fft_impl(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
-                        int x_single, const b200_c64* sens, void* stream, bool native) {
-    ARG_CHECK(p && x && grid && nb >= 1 && nb <= 65535, "pad_fft: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
-    const bool mod = native && native_modulated(p);
-    if (p->fft_variant != 1 && fft256_supported(p->g))
-        return fft256_forward(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
-                              x_single, reinterpret_cast<const float2*>(sens), mod, as_stream(stream));
-    int rc = b200nufft_scale_pad(p, x, grid, nb, apply_sn, x_single, sens, stream);
-    if (rc) return rc;
-    rc = b200nufft_fft(p, grid, nb, 3, stream);
-    if (rc || !mod) return rc;
-    return col3d_modulate(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(grid), nb, 0,
-                          as_stream(stream));
-}
-
 extern "C" int b200nufft_pad_fft(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
                                  int x_single, const b200_c64* sens, void* stream) {
-    return pad_fft_impl(p, x, grid, nb, apply_sn, x_single, sens, stream, false);
+    ARG_CHECK(p && x && grid && nb >= 1 && nb <= 65535, "pad_fft: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (p->fft_variant != 1 && fft256_supported(p->g))
+        return fft256_forward(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
+                              x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
+    int rc = b200nufft_scale_pad(p, x, grid, nb, apply_sn, x_single, sens, stream);
+    if (rc) return rc;
+    return b200nufft_fft(p, grid, nb, 3, stream);
 }
 
 // ifft_crop: x = crop(IFFT(grid)) * f (mode 0/1/2 as crop_scale), optionally combined over coils.
 // The grid is used as scratch: its contents are undefined afterwards.
+// `modulated`: the grid comes from gridding_impl(..., modulated_ok = true) (phase-modulated iff
+// gridding_modulated(p)); the fused inverse passes undo the modulation on the way in.
 static int ifft_crop_impl(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int nb, int mode, int combine,
-                          const b200_c64* sens, void* stream, bool native) {
+                          const b200_c64* sens, void* stream, bool modulated) {
     ARG_CHECK(p && x && grid && nb >= 1 && mode >= 0 && mode <= 2, "ifft_crop: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t st = as_stream(stream);
     const float scale = 1.0f / (float)p->g.Kprod;
-    const bool mod = native && native_modulated(p);
+    const bool mod = modulated && gridding_modulated(p);
     if (p->fft_variant != 1 && fft256_supported(p->g)) {
         if (!combine)
             return fft256_inverse(p, reinterpret_cast<float2*>(grid), reinterpret_cast<float2*>(x), nb, mode, scale,
@@ -341,7 +332,7 @@ static int ifft_crop_impl(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int n
     }
     int rc = B200_OK;
     if (mod) {
-        rc = col3d_modulate(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(grid), nb, 1, st);
+        rc = col3d_demodulate(p, reinterpret_cast<float2*>(grid), nb, st);
         if (rc) return rc;
     }
     rc = b200nufft_fft(p, grid, nb, 4, stream);
@@ -355,26 +346,20 @@ extern "C" int b200nufft_ifft_crop(b200nufft_plan_t p, b200_c64* grid, b200_c64*
                                    const b200_c64* sens, void* stream) {
     return ifft_crop_impl(p, grid, x, nb, mode, combine, sens, stream, false);
 }
-
-// native-grid variants (solvers that keep their k-space vectors in the plan's native form)
-extern "C" int b200nufft_pad_fft_native(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
-                                        int x_single, const b200_c64* sens, void* stream) {
-    return pad_fft_impl(p, x, grid, nb, apply_sn, x_single, sens, stream, true);
-}
-extern "C" int b200nufft_ifft_crop_native(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int nb, int mode,
-                                          int combine, const b200_c64* sens, void* stream) {
+extern "C" int b200nufft_ifft_crop_modulated(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int nb, int mode,
+                                             int combine, const b200_c64* sens, void* stream) {
     return ifft_crop_impl(p, grid, x, nb, mode, combine, sens, stream, true);
 }
-extern "C" int b200nufft_native_is_modulated(b200nufft_plan_t p) { return (p && native_modulated(p)) ? 1 : 0; }
+extern "C" int b200nufft_gridding_is_modulated(b200nufft_plan_t p) { return (p && gridding_modulated(p)) ? 1 : 0; }
 
 static int forward_impl(b200nufft_plan_t p, const float2* x, int x_single, const float2* sens, float2* y, int nb,
                         void* stream) {
     int rc = ensure_scratch(p, nb);
     if (rc) return rc;
-    rc = pad_fft_impl(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
-                      x_single, reinterpret_cast<const b200_c64*>(sens), stream, true);
+    rc = b200nufft_pad_fft(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
+                           x_single, reinterpret_cast<const b200_c64*>(sens), stream);
     if (rc) return rc;
-    return interp_impl(p, p->d_grid, y, nb, as_stream(stream), true);
+    return interp_impl(p, p->d_grid, y, nb, as_stream(stream));
 }
 
 static int adjoint_impl(b200nufft_plan_t p, const float2* y, float2* x, int nb, int combine, const float2* sens,

@@ -241,23 +241,6 @@ class NUFFT:
         _lib.check(self._lib.b200nufft_gridding(self._plan, _ptr(y), _ptr(store), nb, _stream()))
         return view
 
-    # native-grid variants for the solvers: the grid stays in the plan's native form (phase-modulated when the
-    # column-sweep kernels are in use, csrc/col3d.cu), which saves two passes over the grid per G = interp^H interp
-    def _k2y_native(self, k):
-        self._require_plan()
-        store, nb, batched = self._grid_storage(k)
-        y = torch.empty((self.M, nb) if batched else (self.M,), dtype=torch.complex64, device=self.device)
-        _lib.check(self._lib.b200nufft_interp_native(self._plan, _ptr(store), _ptr(y), nb, _stream()))
-        return y
-
-    def _y2k_native(self, y):
-        self._require_plan()
-        y = self._check_dev(y, (self.M,), 'y')
-        nb = self._nb_of(y, 1, 'y')
-        view, store = self._new_grid(nb, y.dim() == 2)
-        _lib.check(self._lib.b200nufft_gridding_native(self._plan, _ptr(y), _ptr(store), nb, _stream()))
-        return view
-
     def _k2xx_device(self, k):
         """Inverse FFT (in place on k when k is a coil-major view, like the reference's in-place FFT) + crop."""
         self._require_plan()
@@ -448,8 +431,16 @@ class NUFFT:
         return (kindx.cpu().numpy().view(numpy.uint32), udata.cpu().numpy(), k0.cpu().numpy(), perm.cpu().numpy(),
                 tuple(int(v) for v in tile[:self.ndims]), tuple(int(v) for v in tile[self.ndims:]))
 
+    def _col_perm(self):
+        """(perm int32 (M,), tile, sub): sweep-order permutation of the column-sweep gridding records and its sort key."""
+        self._require_plan()
+        perm = torch.empty((self.M,), dtype=torch.int32, device=self.device)
+        tile = numpy.zeros(6, dtype=numpy.int32)
+        _lib.check(self._lib.b200nufft_plan_get_col_perm(self._plan, _ptr(perm), tile.ctypes.data, _stream()))
+        return perm.cpu().numpy(), tuple(int(v) for v in tile[:3]), tuple(int(v) for v in tile[3:])
+
     def layout(self):
-        """0: tile / sub-tile bins, 1: column sweep (3-D, J = 6; csrc/col3d.cu)."""
+        """1 if the plan also holds the column-sweep gridding records (3-D, J = 6; csrc/col3d.cu), else 0."""
         self._require_plan()
         return int(self._lib.b200nufft_plan_get_layout(self._plan))
 

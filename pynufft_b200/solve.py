@@ -92,21 +92,19 @@ def cg(nufft, gy, maxiter=30, group=None):
     if group is not None:
         import torch.distributed as dist
         allreduce = lambda t: dist.all_reduce(t, group=group)
-    # k-space vectors stay in the plan's native form: G' = M G M^H with M diagonal and unitary has the same CG
-    # scalars, and x' = M x is undone by the final inverse FFT pass
-    bview = nufft._y2k_native(gy)
+    bview = nufft._y2k_device(gy)
     batched = bview.dim() == nufft.ndims + 1
     nb = int(bview.shape[-1]) if batched else 1
     store = lambda view: nufft._grid_storage(view)[0]          # contiguous storage in the library layout (no copy)
     view = lambda flat: nufft._view_of(flat, nb, batched)
 
     def G(flat):
-        return store(nufft._y2k_native(nufft._k2y_native(view(flat))))
+        return store(nufft._y2k_device(nufft._k2y_device(view(flat))))
 
     xs = cg_kspace(G, store(bview), maxiter, CudaVectorOps(L), allreduce)
     # inverse FFT, crop, divide by sn  (solve_device.py:463-480)
     x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=nufft.device)
-    _lib.check(L.b200nufft_ifft_crop_native(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
+    _lib.check(L.b200nufft_ifft_crop(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
     return x2
 
 

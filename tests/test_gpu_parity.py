@@ -47,8 +47,19 @@ def test_plan_matches_reference(golden, dev):
     assert rel(udata, golden['udata']) < 1e-6
     p = orc.Plan(golden['om'], golden['Nd'], golden['Kd'], golden['Jd'])
     assert numpy.array_equal(k0, p.k0)
-    assert (tile, sub) == orc.default_tiles(golden['Kd'], golden['Jd'])
+    assert (tile, sub) == orc.default_tiles(golden['Kd'])
     assert numpy.array_equal(perm, orc.sort_permutation(p.k0, golden['Kd'], tile, sub))   # bit-exact permutation
+    check_col_perm(A, p.k0, golden['Kd'], golden['Jd'])
+
+
+def check_col_perm(A, k0, Kd, Jd):
+    """second sort of 3-D J = 6 plans (column-sweep gridding records): bit-exact against the oracle's key"""
+    ct = orc.column_sweep_tiles(Kd, Jd)
+    assert A.layout() == (1 if ct else 0)
+    if ct:
+        cperm, ctile, csub = A._col_perm()
+        assert (ctile, csub) == ct
+        assert numpy.array_equal(cperm, orc.sort_permutation(k0, Kd, ctile, csub))
 
 
 # ------------------------------------------------------------------------------ operator vs golden
@@ -159,8 +170,43 @@ def test_ragged_geometries(dev, geom):
         kindx, _, k0, perm, tile, sub = A._plan_arrays()
         assert numpy.array_equal(kindx, O.p.kindx)
         assert numpy.array_equal(perm, orc.sort_permutation(O.p.k0, Kd, tile, sub))
+        check_col_perm(A, O.p.k0, Kd, Jd)
         assert rel(A.forward(x), O.forward(x)) < TOL
         assert rel(A.adjoint(y), O.adjoint(y)) < TOL
+
+
+@pytest.mark.parametrize('geom', [
+    ((32, 32, 32), (64, 64, 64), 20000),
+    ((15, 20, 24), (30, 50, 48), 5000),          # odd N (wrap sign +1) in dim 0, K1 % 4 != 0, K2 % 5 != 0
+    ((8, 8, 8), (16, 16, 16), 300),
+    ((33, 31, 32), (66, 62, 64), 30000),
+    ((5, 4, 5), (6, 9, 10), 200),                # smallest grid the column-sweep kernel takes: its box is the grid
+])
+def test_gridding_kernels_agree_3d(dev, geom):
+    """3-D J = 6: column-sweep (auto), tiled and generic gridding against the oracle, true-grid and fused paths"""
+    Nd, Kd, M = geom
+    Jd = (6, 6, 6)
+    rng = numpy.random.default_rng(3)
+    om = rng.uniform(-numpy.pi, numpy.pi, (M, 3))
+    om[:7] = [[numpy.pi, numpy.pi, numpy.pi], [-numpy.pi, -numpy.pi, -numpy.pi], [0, 0, 0], [numpy.pi, 0, -numpy.pi],
+              [3.1, -3.1, 3.1], [-3.1, 3.1, -3.1], [0.001, -0.001, 3.14]]
+    om[7:107] = om[6]                            # duplicates: 100 samples in one cell
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, Jd)
+    x = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    y = (rng.standard_normal(M) + 1j * rng.standard_normal(M)).astype(numpy.complex64)
+    A = make(dev, om, Nd, Kd, Jd)
+    assert A.layout() == 1
+    check_col_perm(A, O.p.k0, Kd, Jd)
+    ref_k, ref_x = O.y2k(y), O.adjoint(y)
+    for gv in (0, 2, 1):
+        if gv == 2 and min(Kd) < 16:             # the tiled kernels need 16^3 tiles
+            continue
+        A.set_variant(0 if gv != 1 else 1, gv)
+        assert rel(A.y2k(y), ref_k) < TOL
+        assert rel(A.adjoint(y), ref_x) < TOL
+        assert rel(A.selfadjoint(x), O.adjoint(O.forward(x).astype(numpy.complex64))) < TOL
+    A.release()
 
 
 # ------------------------------------------------------------------------------ config 1 (2D 256^2, PROPELLER)

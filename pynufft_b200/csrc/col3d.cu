@@ -81,6 +81,13 @@ __device__ __forceinline__ void red_v2(float2* addr, float2 a) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a.x), "f"(a.y) : "memory");
 }
 
+// cell + off elements as ONE 64-bit multiply-add (the compiler would re-derive the pointer from the grid base)
+__device__ __forceinline__ float2* cell_at(const float2* cell, int off) {
+    float2* r;
+    asm("mad.wide.s32 %0, %1, 8, %2;\n" : "=l"(r) : "r"(off), "l"(cell));
+    return r;
+}
+
 // next work item of this warp (dynamic: one atomic per item, broadcast from lane 0)
 __device__ __forceinline__ int next_item(int* counter, int lane) {
     int it = 0;
@@ -112,10 +119,15 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
     const int c = blockIdx.y;
     float2* gc = grid + (long long)c * g.Kprod;
     const float4* ysc = ys + (long long)c * M;
+    // lanes 30, 31 shadow lane 29's cells with the always-zero record word 30 as their column weight: their
+    // accumulators stay exactly zero and their REDs add 0 to valid cells, so the flush needs no predicate
     const bool active = lane < 3 * CCOLS;
     const int lg = active ? lane / CCOLS : 2;           // row group: box rows lg, lg + 3, lg + 6
     const int lc = active ? lane - CCOLS * lg : CCOLS - 1;   // box column
+    const int lw = active ? lc : CCOLS;                 // word 20 + lw of the record: this lane's column weight
     const int KK = g.K1 * g.K2;
+    const unsigned sbit0 = g.sg0 < 0.f ? 0x80000000u : 0u, sbit1 = g.sg1 < 0.f ? 0x80000000u : 0u,
+                   sbit2 = g.sg2 < 0.f ? 0x80000000u : 0u;
     if (lane == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
@@ -127,25 +139,22 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
     for (int item = next_item(counter + c, lane); item < n_work; item = next_item(counter + c, lane)) {
         const WorkItem wi = work[item];
         const int q1 = wi.tile / g.nq2, q2 = wi.tile - q1 * g.nq2;
-        // this lane's three cells inside a plane, and their wrap signs
-        int roff[CNR];
-        float rsg[CNR];
-        bool wraps = false;
+        // this lane's three cells inside plane 0, and the sign bits of their wrap factors
+        float2* cell[CNR];
+        unsigned rbit[CNR];
         {
             int col = q2 * CT2 + lc;
-            float csg = 1.f;
-            if (col >= g.K2) { col -= g.K2; csg = g.sg2; }
+            unsigned cbit = 0u;
+            if (col >= g.K2) { col -= g.K2; cbit = sbit2; }
 #pragma unroll
             for (int i = 0; i < CNR; ++i) {
                 int row = q1 * CT1 + lg + 3 * i;
-                float s = csg;
-                if (row >= g.K1) { row -= g.K1; s *= g.sg1; }
-                roff[i] = row * g.K2 + col;
-                rsg[i] = s;
-                wraps = wraps || (s != 1.f);
+                unsigned b = cbit;
+                if (row >= g.K1) { row -= g.K1; b ^= sbit1; }
+                cell[i] = gc + (row * g.K2 + col);
+                rbit[i] = b;
             }
         }
-        const bool any_wrap = __any_sync(0xffffffffu, wraps);
         const int nchunks = (wi.end - wi.begin + CCH - 1) / CCH;
         auto issue = [&](int k) {      // lane 0 only
             const int s = wi.begin + k * CCH;
@@ -166,25 +175,32 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
             for (int i = 0; i < CNR; ++i) A[s][i] = make_float2(0.f, 0.f);
         int pbase = -1, slot = 0;       // first plane of the window and its slot (warp-uniform)
 
-        // plane p (slot s) leaves the window: add this lane's cells to the grid (vector REDs), clear the slot
+        // plane p (slot s) leaves the window: add this lane's cells to the grid (vector REDs), clear the slot.
+        // The wrap factors are +-1: applied as sign-bit flips.
+#define COL_FLUSH_SLOT(SS)                                                                         \
+    case SS: {                                                                                     \
+        _Pragma("unroll") for (int i = 0; i < CNR; ++i) {                                          \
+            const unsigned fb = pbit ^ rbit[i];                                                    \
+            const float2 v = make_float2(__uint_as_float(__float_as_uint(A[SS][i].x) ^ fb),        \
+                                         __uint_as_float(__float_as_uint(A[SS][i].y) ^ fb));       \
+            red_v2(cell_at(cell[i], poff), v);                                                     \
+            A[SS][i] = make_float2(0.f, 0.f);                                                      \
+        }                                                                                          \
+    } break;
         auto flush = [&](int s, int p) {
-            float sp = 1.f;
-            if (p >= g.K0) { p -= g.K0; sp = g.sg0; }
-            float2* base = gc + (long long)p * KK;
-            const bool scale = any_wrap || sp != 1.f;
-#pragma unroll
-            for (int ss = 0; ss < 6; ++ss) {
-                if (s == ss) {
-#pragma unroll
-                    for (int i = 0; i < CNR; ++i) {
-                        float2 v = A[ss][i];
-                        if (scale) { const float f = sp * rsg[i]; v.x *= f; v.y *= f; }
-                        if (active) red_v2(base + roff[i], v);
-                        A[ss][i] = make_float2(0.f, 0.f);
-                    }
-                }
+            unsigned pbit = 0u;
+            if (p >= g.K0) { p -= g.K0; pbit = sbit0; }
+            const int poff = p * KK;                    // < prod(Kd) < 2^31
+            switch (s) {
+                COL_FLUSH_SLOT(0)
+                COL_FLUSH_SLOT(1)
+                COL_FLUSH_SLOT(2)
+                COL_FLUSH_SLOT(3)
+                COL_FLUSH_SLOT(4)
+                COL_FLUSH_SLOT(5)
             }
         };
+#undef COL_FLUSH_SLOT
 
         for (int k = 0; k < nchunks; ++k) {
             const int ns = min(CCH, wi.end - (wi.begin + k * CCH));
@@ -203,7 +219,7 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
                 const float4 C1 = *reinterpret_cast<const float4*>(R + 4 * lg);       // c1 of rows lg, lg+3, lg+6
                 const float4 C0a = *reinterpret_cast<const float4*>(R + 12);          // c0rot[0..3]
                 const float4 C0b = *reinterpret_cast<const float4*>(R + 16);          // c0rot[4..5], p0, p0 mod 6
-                const float w = R[20 + lc];
+                const float w = R[20 + lw];
                 const float2 yv = *reinterpret_cast<const float2*>(Y + u);            // conj(P'') * y
                 const int p0 = __float_as_int(C0b.z);
                 if (p0 != pbase) {                        // warp-uniform: the window moved
@@ -292,14 +308,14 @@ static int col_counters(b200nufft_plan_t p, int nb, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(p->d_ccount, 0, sizeof(int) * nb, st));
     return B200_OK;
 }
-// CTAs per coil of the persistent kernel: all SMs x 6 resident CTAs, shared between the coils of the launch
+// CTAs per coil of the persistent kernel: all SMs x 5 resident CTAs, shared between the coils of the launch
 static int col_ctas(b200nufft_plan_t p, int nb) {
     if (p->n_sm == 0) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) p->n_sm = prop.multiProcessorCount;
         if (p->n_sm <= 0) p->n_sm = 148;
     }
-    return std::max(1, (p->n_sm * 6 + nb - 1) / nb);
+    return std::max(1, (p->n_sm * 5 + nb - 1) / nb);
 }
 
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st) {

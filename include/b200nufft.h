@@ -140,6 +140,16 @@ int b200nufft_forward_host(b200nufft_plan_t plan, const b200_c64* x_host, b200_c
                            int nb, void* stream);
 int b200nufft_adjoint_host(b200nufft_plan_t plan, const b200_c64* y_host, b200_c64* x_host,
                            int nb, void* stream);
+/* Pipelined variants for streams of host arrays: the H2D copy, the operator (on `stream`) and the D2H copy of
+ * successive calls overlap (two copy streams inside the plan, chained by events); `slot` (0 or 1) selects one of two
+ * staging buffers per direction.  Nothing blocks the host: call host_wait(op, slot) (op 0 forward, 1 adjoint) before
+ * reading the output of, or reusing the host buffers handed to, the last call on that (op, slot).  Host buffers must
+ * be pinned for the copies to overlap.  */
+int b200nufft_forward_host_async(b200nufft_plan_t plan, const b200_c64* x_host, b200_c64* y_host, int nb, int slot,
+                                 void* stream);
+int b200nufft_adjoint_host_async(b200nufft_plan_t plan, const b200_c64* y_host, b200_c64* x_host, int nb, int slot,
+                                 void* stream);
+int b200nufft_host_wait(b200nufft_plan_t plan, int op, int slot);
 
 /* ---- solver vector ops (fused replacements of the element-wise kernels the device solvers
  *      launch one by one, linalg/solve_device.py:351-481 and :74-275) --------------------------

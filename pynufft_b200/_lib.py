@@ -47,6 +47,9 @@ SIGNATURES = {
     'b200nufft_tv_rhs': (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp]),
     'b200nufft_tv_shrink': (_i, [_vp, _vp, _vp, _vp, _f, _vp]),
     'b200nufft_tv_bregman': (_i, [_vp, _vp, _vp, _i64, _vp]),
+    'b200nufft_forward_host_async': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    'b200nufft_adjoint_host_async': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    'b200nufft_host_wait': (_i, [_vp, _i, _i]),
     'b200nufft_set_variant': (_i, [_vp, _i, _i]),
     'b200nufft_set_layout_preference': (_i, [_i]),
     'b200nufft_plan_get_layout': (_i, [_vp]),

@@ -145,6 +145,15 @@ struct b200nufft_plan_s {
     float2* d_xin = nullptr;
     float2* d_yio = nullptr;
     int io_nb = 0;
+    // pipelined host entry points (stages.cu): copy streams, per-(direction, slot) staging buffers and events
+    struct HostPipe {
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        float2* d_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [0 forward | 1 adjoint][slot]
+        float2* d_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+        cudaEvent_t ev_in[2][2], ev_comp[2][2], ev_out[2][2];
+        int nb = 0;
+        bool ready = false;
+    } pipe;
     // cuFFT
     cufftHandle fft = 0;
     int fft_nb = 0;

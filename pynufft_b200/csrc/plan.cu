@@ -549,9 +549,12 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     return B200_OK;
 }
 
+void host_pipe_destroy(b200nufft_plan_t p);   // stages.cu
+
 extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     if (!p) return B200_OK;
     cudaSetDevice(p->device);
+    host_pipe_destroy(p);
     cudaFree(p->d_pc);
     cudaFree(p->d_om);
     cudaFree(p->d_perm);

@@ -440,3 +440,103 @@ extern "C" int b200nufft_adjoint_host(b200nufft_plan_t p, const b200_c64* y_host
     CUDA_TRY(cudaStreamSynchronize(st));
     return B200_OK;
 }
+
+// ---- pipelined host entry points ------------------------------------------------------------------------------
+// forward_host / adjoint_host above serialise copy-in, compute and copy-out.  The *_host_async pair overlaps them
+// across calls: H2D on a copy-in stream, the operator on the caller's stream, D2H on a copy-out stream, chained by
+// events, with two staging slots per direction; nothing blocks the host until b200nufft_host_wait(op, slot).
+void host_pipe_destroy(b200nufft_plan_t p) {
+    b200nufft_plan_s::HostPipe& h = p->pipe;
+    for (int o = 0; o < 2; ++o)
+        for (int s = 0; s < 2; ++s) {
+            cudaFree(h.d_in[o][s]);
+            cudaFree(h.d_out[o][s]);
+            h.d_in[o][s] = h.d_out[o][s] = nullptr;
+            if (h.ready) {
+                cudaEventDestroy(h.ev_in[o][s]);
+                cudaEventDestroy(h.ev_comp[o][s]);
+                cudaEventDestroy(h.ev_out[o][s]);
+            }
+        }
+    if (h.ready) {
+        cudaStreamDestroy(h.s_in);
+        cudaStreamDestroy(h.s_out);
+    }
+    h.ready = false;
+    h.nb = 0;
+}
+
+static int ensure_pipe(b200nufft_plan_t p, int nb) {
+    b200nufft_plan_s::HostPipe& h = p->pipe;
+    if (!h.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h.s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h.s_out, cudaStreamNonBlocking));
+        for (int o = 0; o < 2; ++o)
+            for (int s = 0; s < 2; ++s) {
+                CUDA_TRY(cudaEventCreateWithFlags(&h.ev_in[o][s], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&h.ev_comp[o][s], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&h.ev_out[o][s], cudaEventDisableTiming));
+            }
+        h.ready = true;
+    }
+    if (h.nb >= nb) return B200_OK;
+    CUDA_TRY(cudaDeviceSynchronize());                  // nothing may still use the old buffers
+    const size_t xb = sizeof(float2) * p->g.Nprod * nb, yb = sizeof(float2) * std::max<long long>(p->M, 1) * nb;
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(h.d_in[0][s]); cudaFree(h.d_out[0][s]); cudaFree(h.d_in[1][s]); cudaFree(h.d_out[1][s]);
+        h.d_in[0][s] = h.d_out[0][s] = h.d_in[1][s] = h.d_out[1][s] = nullptr;
+        h.nb = 0;
+        CUDA_TRY(cudaMalloc(&h.d_in[0][s], xb));        // forward: x in, y out
+        CUDA_TRY(cudaMalloc(&h.d_out[0][s], yb));
+        CUDA_TRY(cudaMalloc(&h.d_in[1][s], yb));        // adjoint: y in, x out
+        CUDA_TRY(cudaMalloc(&h.d_out[1][s], xb));
+    }
+    h.nb = nb;
+    return B200_OK;
+}
+
+static int host_async(b200nufft_plan_t p, int op, const b200_c64* in_host, b200_c64* out_host, int nb, int slot,
+                      void* stream) {
+    ARG_CHECK(p && in_host && out_host && nb >= 1 && (slot == 0 || slot == 1), "host_async: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = ensure_pipe(p, nb);
+    if (rc) return rc;
+    rc = ensure_scratch(p, nb);
+    if (rc) return rc;
+    b200nufft_plan_s::HostPipe& h = p->pipe;
+    cudaStream_t st = as_stream(stream);
+    const size_t xb = sizeof(float2) * p->g.Nprod * nb, yb = sizeof(float2) * p->M * nb;
+    const size_t inb = op == 0 ? xb : yb, outb = op == 0 ? yb : xb;
+    // copy-in: after the operator that last read this slot's input
+    CUDA_TRY(cudaStreamWaitEvent(h.s_in, h.ev_comp[op][slot], 0));
+    if (inb) CUDA_TRY(cudaMemcpyAsync(h.d_in[op][slot], in_host, inb, cudaMemcpyHostToDevice, h.s_in));
+    CUDA_TRY(cudaEventRecord(h.ev_in[op][slot], h.s_in));
+    // operator: after its input arrived and the previous result of this slot left
+    CUDA_TRY(cudaStreamWaitEvent(st, h.ev_in[op][slot], 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, h.ev_out[op][slot], 0));
+    rc = op == 0 ? forward_impl(p, h.d_in[0][slot], 0, nullptr, h.d_out[0][slot], nb, stream)
+                 : adjoint_impl(p, h.d_in[1][slot], h.d_out[1][slot], nb, 0, nullptr, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h.ev_comp[op][slot], st));
+    // copy-out
+    CUDA_TRY(cudaStreamWaitEvent(h.s_out, h.ev_comp[op][slot], 0));
+    if (outb) CUDA_TRY(cudaMemcpyAsync(out_host, h.d_out[op][slot], outb, cudaMemcpyDeviceToHost, h.s_out));
+    CUDA_TRY(cudaEventRecord(h.ev_out[op][slot], h.s_out));
+    return B200_OK;
+}
+
+extern "C" int b200nufft_forward_host_async(b200nufft_plan_t p, const b200_c64* x_host, b200_c64* y_host, int nb,
+                                            int slot, void* stream) {
+    return host_async(p, 0, x_host, y_host, nb, slot, stream);
+}
+extern "C" int b200nufft_adjoint_host_async(b200nufft_plan_t p, const b200_c64* y_host, b200_c64* x_host, int nb,
+                                            int slot, void* stream) {
+    return host_async(p, 1, y_host, x_host, nb, slot, stream);
+}
+extern "C" int b200nufft_host_wait(b200nufft_plan_t p, int op, int slot) {
+    ARG_CHECK(p && (op == 0 || op == 1) && (slot == 0 || slot == 1), "host_wait: bad arguments");
+    if (!p->pipe.ready) return B200_OK;
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaEventSynchronize(p->pipe.ev_out[op][slot]));
+    return B200_OK;
+}

@@ -66,6 +66,7 @@ class NUFFT:
         self.processor = 'hsa'
         self.verbosity = 0
         self._plan = None
+        self._inflight = {}
         self.Nd = self.Kd = self.Jd = ()
         self.ndims = 0
         self.ft_axes = ()
@@ -150,8 +151,9 @@ class NUFFT:
 
     def release(self):
         if getattr(self, '_plan', None) is not None:
-            self._lib.b200nufft_plan_destroy(self._plan)
+            self._lib.b200nufft_plan_destroy(self._plan)      # synchronises the pipelined host copies
             self._plan = None
+        self._inflight = {}
         self._sense = None
 
     # ------------------------------------------------------------------ helpers
@@ -365,25 +367,47 @@ class NUFFT:
             raise ValueError('%s must be a C-contiguous complex64 array of shape %s' % (what, tuple(shape)))
         return out
 
-    def forward(self, x, out=None):
-        """Host forward NUFFT (reference: _forward_host).  `out` may be a preallocated (pinned) array."""
+    def forward(self, x, out=None, slot=None):
+        """Host forward NUFFT (reference: _forward_host).  `out` may be a preallocated (pinned) array.
+
+        slot=None: blocking, like the reference.  slot=0/1: pipelined -- the call only enqueues H2D copy, operator
+        and D2H copy (they overlap with the neighbouring calls' copies and kernels) and returns `out` immediately;
+        call wait('forward', slot) before reading it or reusing x / out.  Use pinned arrays and alternate the slots."""
         self._require_plan()
         x = self._host_c64(x, self.Nd, 'x')
         nb = x.shape[-1] if x.ndim == self.ndims + 1 else 1
         y = self._host_out(out, (self.M, nb) if x.ndim == self.ndims + 1 else (self.M,), 'out')
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.b200nufft_forward_host(self._plan, x.ctypes.data, y.ctypes.data, nb, _stream()))
+            if slot is None:
+                _lib.check(self._lib.b200nufft_forward_host(self._plan, x.ctypes.data, y.ctypes.data, nb, _stream()))
+            else:
+                self._inflight[(0, int(slot))] = (x, y)      # keep the host arrays alive until wait()
+                _lib.check(self._lib.b200nufft_forward_host_async(self._plan, x.ctypes.data, y.ctypes.data, nb,
+                                                                  int(slot), _stream()))
         return y
 
-    def adjoint(self, y, out=None):
-        """Host adjoint NUFFT (reference: _adjoint_host)."""
+    def adjoint(self, y, out=None, slot=None):
+        """Host adjoint NUFFT (reference: _adjoint_host).  slot: as in forward (wait('adjoint', slot))."""
         self._require_plan()
         y = self._host_c64(y, (self.M,), 'y')
         nb = y.shape[-1] if y.ndim == 2 else 1
         x = self._host_out(out, tuple(self.Nd) + ((nb,) if y.ndim == 2 else ()), 'out')
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.b200nufft_adjoint_host(self._plan, y.ctypes.data, x.ctypes.data, nb, _stream()))
+            if slot is None:
+                _lib.check(self._lib.b200nufft_adjoint_host(self._plan, y.ctypes.data, x.ctypes.data, nb, _stream()))
+            else:
+                self._inflight[(1, int(slot))] = (y, x)
+                _lib.check(self._lib.b200nufft_adjoint_host_async(self._plan, y.ctypes.data, x.ctypes.data, nb,
+                                                                  int(slot), _stream()))
         return x
+
+    def wait(self, op, slot):
+        """Block until the last pipelined forward / adjoint on `slot` has delivered its output to the host."""
+        self._require_plan()
+        o = {'forward': 0, 'adjoint': 1}[op]
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b200nufft_host_wait(self._plan, o, int(slot)))
+        self._inflight.pop((o, int(slot)), None)
 
     def selfadjoint(self, x):
         return self.to_host(self._selfadjoint_device(self.to_device(x)))

@@ -337,12 +337,12 @@ def run_ours(args, rank, world, local_rank):
     kern['pad_fft'] = timed(lambda: lib.b200nufft_pad_fft(A._plan, P(x.data_ptr()), P(grid.data_ptr()), 1, 1, 0, None, st()), kit, 3) / kit
     kern['interp'] = timed(lambda: lib.b200nufft_interp(A._plan, P(grid.data_ptr()), P(yv.data_ptr()), 1, st()), kit, 3) / kit
     # the adjoint's own pair of stages: the column-sweep gridding leaves the grid phase-modulated and the fused inverse
-    # passes undo it (csrc/col3d.cu); "gridding" = sorted-data pre-gather + scatter kernel, without the grid memset
-    kern['gridding_incl_memset'] = timed(lambda: lib.b200nufft_gridding_modulated(A._plan, P(yv.data_ptr()), P(grid.data_ptr()), 1, st()), kit, 3) / kit
+    # passes undo it (csrc/col3d.cu); "gridding" = the whole stage: grid zero-fill (on a side stream) beside the
+    # sorted-data pre-gather, then the scatter kernel
+    kern['gridding'] = timed(lambda: lib.b200nufft_gridding_modulated(A._plan, P(yv.data_ptr()), P(grid.data_ptr()), 1, st()), kit, 3) / kit
     kern['memset_grid'] = timed(lambda: grid.zero_(), kit, 3) / kit
     kern['ifft_crop'] = timed(lambda: lib.b200nufft_ifft_crop_modulated(A._plan, P(grid.data_ptr()), P(xo.data_ptr()), 1, 1, 0, None, st()), kit, 3) / kit
-    kern['gridding'] = kern['gridding_incl_memset'] - kern['memset_grid']
-    kern['gridding_true_grid_incl_memset'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(yv.data_ptr()), P(grid.data_ptr()), 1, st()), kit, 3) / kit
+    kern['gridding_true_grid'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(yv.data_ptr()), P(grid.data_ptr()), 1, st()), kit, 3) / kit
     peak, peak_src = measured_peak()
     dom = 'gridding' if kern['gridding'] >= kern['interp'] else 'interp'
     achieved = ALGO_BYTES / (kern[dom] * 1e-3) / 1e9

@@ -9,8 +9,9 @@ What is recorded per case (all produced by reference code, none by this repo):
   * helper.plan(format='pELL'): kindx, udata, meshindex, tensor_sn, alpha   (src/_helper/helper.py:620-802)
   * NUFFT() CPU operator: forward(x), adjoint(y), selfadjoint(x) and the six stages
     (nufft/_nufft_class_methods_cpu.py:168-362)
-  * selfadjoint2 (Toeplitz-style approximation, _nufft_class_methods_cpu.py:127-146) and solve(..., 'dc')
-    (linalg/solve_cpu.py:165-225)
+  * selfadjoint2 (Toeplitz-style approximation, _nufft_class_methods_cpu.py:127-146), solve(..., 'dc')
+    (linalg/solve_cpu.py:165-225) and the scipy Krylov family solve(..., 'lsmr' | 'lsqr' | 'bicgstab' | 'gmres')
+    (linalg/solve_cpu.py:226-288)
   * the reference's *device* solvers (linalg/solve_device.py: cg, L1TVOLS) executed on a
     numpy mock of the reikna thread/program objects, so the real solver control flow is
     what pins oracle.solve_cg / oracle.solve_l1tvols.
@@ -205,6 +206,11 @@ def run_case(name, om, Nd, Kd, Jd, seed, solvers=False):
         out['l1tvols5'] = numpy.asarray(solve_device.solve(dev, garr(y), 'L1TVOLS', maxiter=5, rho=2)).astype(c64)
         from reference.linalg import solve_cpu
         out['dc2'] = numpy.asarray(solve_cpu.solve(A, y, 'dc', 2)).astype(c64)       # linalg/solve_cpu.py:165-225
+        # scipy Krylov family of the CPU solve (linalg/solve_cpu.py:226-288), few iterations, fixed counts
+        out['lsmr6'] = numpy.asarray(solve_cpu.solve(A, y, 'lsmr', maxiter=6)).astype(c64)
+        out['lsqr6'] = numpy.asarray(solve_cpu.solve(A, y, 'lsqr', iter_lim=6)).astype(c64)
+        out['bicgstab3'] = numpy.asarray(solve_cpu.solve(A, y, 'bicgstab', maxiter=3)).astype(c64)
+        out['gmres1'] = numpy.asarray(solve_cpu.solve(A, y, 'gmres', maxiter=1, restart=4)).astype(c64)
     path = os.path.join(OUT, name + '.npz')
     numpy.savez_compressed(path, **out)
     print(name, 'M=%d' % M, '%.1f KB' % (os.path.getsize(path) / 1024))

@@ -434,6 +434,24 @@ def solve_cg(nufft, y, maxiter=30, dtype=numpy.complex64):
     return (x2 / sn).astype(c)
 
 
+def solve_krylov(nufft, y, solver, *args, **kwargs):
+    """The scipy Krylov family of the CPU solve, linalg/solve_cpu.py:226-288: 'lsmr' / 'lsqr' on the rectangular
+    interpolator A = k2y (rmatvec y2k), everything else ('bicgstab', 'bicg', 'gmres', 'lgmres', scipy 'cg') on
+    G = y2k . k2y with right-hand side y2k(y); the k-space solution goes through k2xx and is DIVIDED by sn."""
+    import scipy.sparse.linalg as sla
+    Kd, K, M = tuple(nufft.Kd), nufft.Kdprod, nufft.M
+    if solver in ('lsmr', 'lsqr'):
+        A = sla.LinearOperator((M, K), matvec=lambda k: nufft.k2y(k.reshape(Kd)).ravel(),
+                               rmatvec=lambda v: nufft.y2k(v.reshape(M)).ravel(), dtype=numpy.complex128)
+        vec = {'lsmr': sla.lsmr, 'lsqr': sla.lsqr}[solver](A, numpy.asarray(y).ravel(), *args, **kwargs)[0]
+    else:
+        G = lambda k: nufft.y2k(nufft.k2y(k.reshape(Kd))).ravel()
+        A = sla.LinearOperator((K, K), matvec=G, rmatvec=G, dtype=numpy.complex128)
+        methods = {'cg': sla.cg, 'bicgstab': sla.bicgstab, 'bicg': sla.bicg, 'gmres': sla.gmres, 'lgmres': sla.lgmres}
+        vec = methods[solver](A, nufft.y2k(y).ravel(), *args, **kwargs)[0]
+    return nufft.k2xx(vec.reshape(Kd)) / nufft.sn
+
+
 def solve_dc(nufft, y, maxiter=1):
     """'dc' (Pipe density compensation), linalg/solve_cpu.py:165-225: W = 1; W <- W / (A A^H W) `maxiter`
     times; x = A^H (W y)."""

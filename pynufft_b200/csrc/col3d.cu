@@ -332,7 +332,20 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
         CUDA_TRY(cudaFuncSetAttribute(k_gridding_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
         p->attr_col = true;
     }
-    if (p->n_cwork == 0) return B200_OK;
+    // the grid is zeroed on a side stream while this stream pre-gathers the sorted data; the scatter waits for both
+    if (!p->s_side) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->s_side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(p->ev_fork, st));          // everything that used the grid before is ordered first
+    CUDA_TRY(cudaStreamWaitEvent(p->s_side, p->ev_fork, 0));
+    CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, p->s_side));
+    CUDA_TRY(cudaEventRecord(p->ev_join, p->s_side));
+    if (p->n_cwork == 0) {
+        CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join, 0));
+        return B200_OK;
+    }
     if (p->ys_nb < nb) {
         if (p->d_ys) { CUDA_TRY(cudaFree(p->d_ys)); p->d_ys = nullptr; p->ys_nb = 0; }
         CUDA_TRY(cudaMalloc(&p->d_ys, sizeof(float4) * p->M * nb));
@@ -345,6 +358,7 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
     }
     int rc = col_counters(p, nb, st);
     if (rc) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join, 0));
     dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb)), nb);
     k_gridding_col<<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
                                                                  p->d_crec, p->d_ys, p->M, grid);

@@ -119,13 +119,13 @@ int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaS
 // modulated_ok: the caller takes the grid phase-modulated when the column-sweep kernel ran (gridding_modulated(p));
 // otherwise the true grid is returned (one extra pass after the column-sweep kernel).
 int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool modulated_ok) {
-    CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
-    if (p->M == 0) return B200_OK;
-    if (gridding_modulated(p)) {
+    if (p->M > 0 && gridding_modulated(p)) {         // zeroes the grid itself, overlapped with its pre-gather
         int rc = col3d_gridding(p, y, grid, nb, st);
         if (rc || modulated_ok) return rc;
         return col3d_demodulate(p, grid, nb, st);
     }
+    CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
+    if (p->M == 0) return B200_OK;
     if (use_bi(p, nb)) return batch2d_gridding(p, y, grid, nb, st);
     if (p->gridding_variant != 1 && single2d_supported(p->g)) return single2d_gridding(p, y, grid, nb, st);
     if (p->gridding_variant != 1 && tiled_supported(p->g)) return gridding_tiled_launch(p, y, grid, nb, st);

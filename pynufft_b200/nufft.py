@@ -92,8 +92,11 @@ class NUFFT:
         nd = len(Nd)
         if ft_axes is not None and tuple(ft_axes) != tuple(range(nd)):
             raise NotImplementedError('partial ft_axes is unsupported (broken upstream, SURVEY.md 8c)')
-        if radix not in (None, 1):
-            raise NotImplementedError('radix > 1 is out of scope (SURVEY.md 8f)')
+        # radix (helper.py:497-556, doc/source/manu/variable_radix.rst) only regroups the reference's pELL storage
+        # (products of `radix` dimensions pre-multiplied to save in-kernel multiplies); results are identical.  The
+        # plan here always keeps per-dimension REAL factors, so any valid radix is accepted and changes nothing.
+        if radix is not None and not (isinstance(radix, (int, numpy.integer)) and 1 <= int(radix) <= max(nd, 1)):
+            raise ValueError('radix must be an integer in 1..%d' % max(nd, 1))
         if nd > _lib.MAX_DIM:
             raise NotImplementedError('ndim <= 3 supported')
         self.release()

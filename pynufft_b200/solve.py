@@ -170,12 +170,48 @@ def density_compensation(nufft, gy, maxiter=1):
     return nufft._adjoint_device(W * gy)
 
 
+KRYLOV = ('lsmr', 'lsqr', 'bicgstab', 'bicg', 'gmres', 'lgmres')
+
+
+def krylov(nufft, gy, solver, *args, **kwargs):
+    """The scipy Krylov family of the reference's CPU solve (linalg/solve_cpu.py:226-288) with the
+    device operator as the matvec: 'lsmr' / 'lsqr' on A = k2y (rmatvec y2k), the others on G = y2k . k2y with
+    right-hand side y2k(y); then k2xx and DIVIDE by sn.  scipy runs the recurrences on the host exactly as in the
+    reference (extra positional / keyword arguments go to the scipy routine); every operator application runs on
+    the GPU, its k-space / data vector crossing PCIe once each way.  Single coil."""
+    import scipy.sparse.linalg as sla
+    if nufft.batch not in (None, 1) or gy.dim() != 1:
+        raise ValueError('the scipy Krylov solvers are single-coil (as the reference CPU object)')
+    Kd, K, M = tuple(nufft.Kd), int(nufft.Kdprod), int(nufft.M)
+    c64 = numpy.complex64
+    dev = lambda a, shape: nufft.to_device(numpy.ascontiguousarray(numpy.asarray(a).reshape(shape), dtype=c64))
+    k2y = lambda k: nufft.to_host(nufft._k2y_device(dev(k, Kd))).ravel()
+    y2k = lambda v: nufft.to_host(nufft._y2k_device(dev(v, (M,)))).ravel()
+    if solver in ('lsmr', 'lsqr'):
+        A = sla.LinearOperator((M, K), matvec=k2y, rmatvec=y2k, dtype=numpy.complex128)
+        vec = {'lsmr': sla.lsmr, 'lsqr': sla.lsqr}[solver](A, nufft.to_host(gy).ravel(), *args, **kwargs)[0]
+    else:
+        G = lambda k: y2k(k2y(k))
+        A = sla.LinearOperator((K, K), matvec=G, rmatvec=G, dtype=numpy.complex128)
+        methods = {'bicgstab': sla.bicgstab, 'bicg': sla.bicg, 'gmres': sla.gmres, 'lgmres': sla.lgmres}
+        vec = methods[solver](A, nufft.to_host(nufft._y2k_device(gy)).ravel(), *args, **kwargs)[0]
+    ks = dev(vec, Kd)
+    x2 = torch.empty(tuple(nufft.Nd), dtype=torch.complex64, device=nufft.device)
+    _lib.check(nufft._lib.b200nufft_ifft_crop(nufft._plan, _ptr(nufft._grid_storage(ks)[0]), _ptr(x2), 1, 2, 0, None,
+                                              _stream()))
+    return x2
+
+
 def solve(nufft, gy, solver=None, maxiter=30, *args, **kwargs):
-    """solve(nufft, y, solver, maxiter, **kw) -- linalg/solve_device.py:312."""
+    """solve(nufft, y, solver, maxiter, **kw) -- linalg/solve_device.py:312; plus the CPU solve's scipy family."""
+    if solver in KRYLOV:
+        if 'maxiter' not in kwargs and solver != 'lsqr' and maxiter != 30:
+            kwargs['maxiter'] = maxiter
+        return krylov(nufft, gy, solver, *args, **kwargs)
     if solver == 'cg':
         return cg(nufft, gy, maxiter=maxiter, **kwargs)
     if solver == 'L1TVOLS':
         return L1TVOLS(nufft, gy, maxiter=maxiter, *args, **kwargs)
     if solver == 'dc':
         return density_compensation(nufft, gy, maxiter=maxiter)
-    raise ValueError("solver must be 'cg', 'L1TVOLS' or 'dc' (got %r)" % (solver,))
+    raise ValueError("solver must be 'cg', 'L1TVOLS', 'dc' or one of %s (got %r)" % (', '.join(KRYLOV), solver))

@@ -94,9 +94,28 @@ def test_solvers_match_reference_device_algorithms(golden, dev):
     assert rel(A.solve(y, 'cg', maxiter=10), golden['cg10']) < 1e-4
     assert rel(A.solve(y, 'L1TVOLS', maxiter=5, rho=2), golden['l1tvols5']) < 1e-4
     assert rel(A.solve(y, 'dc', maxiter=2), golden['dc2']) < 1e-4
+    # the CPU solve's scipy Krylov family driving the device operator
+    assert rel(A.solve(y, 'lsmr', maxiter=6), golden['lsmr6']) < 1e-4
+    assert rel(A.solve(y, 'lsqr', iter_lim=6), golden['lsqr6']) < 1e-4
+    assert rel(A.solve(y, 'bicgstab', maxiter=3), golden['bicgstab3']) < 1e-4
+    assert rel(A.solve(y, 'gmres', maxiter=1, restart=4), golden['gmres1']) < 1e-4
 
 
 # ------------------------------------------------------------------------------ edge cases
+def test_radix_is_accepted_and_changes_nothing(golden, dev):
+    """radix regroups the reference's coefficient storage only"""
+    import pynufft_b200
+    nd = len(golden['Nd'])
+    for radix in range(1, nd + 1):
+        A = pynufft_b200.NUFFT(dev)
+        assert A.plan(golden['om'], golden['Nd'], golden['Kd'], golden['Jd'], radix=radix) == 0
+        assert rel(A.forward(golden['x']), golden['forward']) < TOL
+        assert rel(A.adjoint(golden['y_in']), golden['adjoint']) < TOL
+        A.release()
+    with pytest.raises(ValueError):
+        pynufft_b200.NUFFT(dev).plan(golden['om'], golden['Nd'], golden['Kd'], golden['Jd'], radix=nd + 1)
+
+
 def test_argument_errors(dev):
     import pynufft_b200
     A = pynufft_b200.NUFFT(dev)

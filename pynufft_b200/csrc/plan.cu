@@ -242,6 +242,13 @@ __global__ void k_export(Geom g, const PlanConst* __restrict__ pc, const double*
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// plan-time temporaries: freed on every exit path
+struct DevTmp {
+    void* p = nullptr;
+    ~DevTmp() { cudaFree(p); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
 static void choose_tiles(Geom& g) {
     // tile edge per dim: the bin key of the sort contract.  3-D: 16^3 (staged box 21^3 for J=6),
     // 2-D: 32^2, 1-D: 256; never larger than K.
@@ -373,11 +380,11 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
 
     std::vector<int> h_bin_start(p->n_bins + 1, 0);
     if (M > 0) {
-        int *d_keys = nullptr, *d_keys_s = nullptr, *d_vals = nullptr;
-        void* d_tmp = nullptr;
-        PLAN_TRY(cudaMalloc(&d_keys, sizeof(int) * M));
-        PLAN_TRY(cudaMalloc(&d_keys_s, sizeof(int) * M));
-        PLAN_TRY(cudaMalloc(&d_vals, sizeof(int) * M));
+        DevTmp t_keys, t_keys_s, t_vals, t_tmp;
+        PLAN_TRY(cudaMalloc(&t_keys.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_keys_s.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_vals.p, sizeof(int) * M));
+        int *d_keys = t_keys.as<int>(), *d_keys_s = t_keys_s.as<int>(), *d_vals = t_vals.as<int>();
         const int TB = 256;
         const unsigned nblk = (unsigned)((M + TB - 1) / TB);
         k_bin_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, d_keys, d_vals);
@@ -388,8 +395,8 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         size_t tmp_bytes = 0;
         PLAN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_perm,
                                                  (int)M, 0, end_bit, st));
-        PLAN_TRY(cudaMalloc(&d_tmp, tmp_bytes));
-        PLAN_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_perm,
+        PLAN_TRY(cudaMalloc(&t_tmp.p, tmp_bytes));
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(t_tmp.p, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_perm,
                                                  (int)M, 0, end_bit, st));   // stable LSD radix sort
         k_bin_start<<<(p->n_bins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, p->n_bins, p->d_bin_start);
         g_launches++;
@@ -400,10 +407,6 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         PLAN_TRY(cudaMemcpyAsync(h_bin_start.data(), p->d_bin_start, sizeof(int) * (p->n_bins + 1),
                                  cudaMemcpyDeviceToHost, st));
         PLAN_TRY(cudaStreamSynchronize(st));
-        cudaFree(d_keys);
-        cudaFree(d_keys_s);
-        cudaFree(d_vals);
-        cudaFree(d_tmp);
     } else {
         PLAN_TRY(cudaMemsetAsync(p->d_bin_start, 0, sizeof(int) * (p->n_bins + 1), st));
         PLAN_TRY(cudaStreamSynchronize(st));
@@ -488,12 +491,12 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
             PLAN_TRY(cudaMemcpyAsync(p->d_mod, hm.data(), sizeof(float2) * hm.size(), cudaMemcpyHostToDevice, st));
             PLAN_TRY(cudaStreamSynchronize(st));
         }
-        int *d_keys = nullptr, *d_keys_s = nullptr, *d_vals = nullptr, *d_cbin = nullptr;
-        void* d_tmp = nullptr;
-        PLAN_TRY(cudaMalloc(&d_keys, sizeof(int) * M));
-        PLAN_TRY(cudaMalloc(&d_keys_s, sizeof(int) * M));
-        PLAN_TRY(cudaMalloc(&d_vals, sizeof(int) * M));
-        PLAN_TRY(cudaMalloc(&d_cbin, sizeof(int) * (n_cbins + 1)));
+        DevTmp t_keys, t_keys_s, t_vals, t_cbin, t_tmp;
+        PLAN_TRY(cudaMalloc(&t_keys.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_keys_s.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_vals.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_cbin.p, sizeof(int) * (n_cbins + 1)));
+        int *d_keys = t_keys.as<int>(), *d_keys_s = t_keys_s.as<int>(), *d_vals = t_vals.as<int>(), *d_cbin = t_cbin.as<int>();
         const int TB = 256;
         const unsigned nblk = (unsigned)((M + TB - 1) / TB);
         k_col_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, col_nq2, d_keys, d_vals);
@@ -504,8 +507,8 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         size_t tmp_bytes = 0;
         PLAN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_cperm, (int)M, 0,
                                                  end_bit, st));
-        PLAN_TRY(cudaMalloc(&d_tmp, tmp_bytes));
-        PLAN_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_cperm, (int)M, 0,
+        PLAN_TRY(cudaMalloc(&t_tmp.p, tmp_bytes));
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(t_tmp.p, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_cperm, (int)M, 0,
                                                  end_bit, st));
         k_bin_start<<<(n_cbins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, n_cbins, d_cbin);
         g_launches++;
@@ -516,11 +519,6 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         std::vector<int> h_cbin(n_cbins + 1, 0);
         PLAN_TRY(cudaMemcpyAsync(h_cbin.data(), d_cbin, sizeof(int) * (n_cbins + 1), cudaMemcpyDeviceToHost, st));
         PLAN_TRY(cudaStreamSynchronize(st));
-        cudaFree(d_keys);
-        cudaFree(d_keys_s);
-        cudaFree(d_vals);
-        cudaFree(d_cbin);
-        cudaFree(d_tmp);
         // every column's samples (already in plane order) are cut into segments of at most COL_SEG samples; items
         // stay in column order (q2 fastest), so that columns whose halos overlap run close in time
         std::vector<WorkItem> cw;

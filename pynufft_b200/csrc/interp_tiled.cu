@@ -204,20 +204,22 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float* R = srec + (b * 8 + u) * SRW;
-                const int base = __float_as_int(R[18]);
                 const float w01 = R[j0l] * R[6 + j1l];
                 const float4 C0 = *reinterpret_cast<const float4*>(R + 12);
-                const float2 C1 = *reinterpret_cast<const float2*>(R + 16);
+                const float4 C1b = *reinterpret_cast<const float4*>(R + 16);          // c2[4], c2[5], base, perm
+                const int base = __float_as_int(C1b.z);
+                const float2 C1 = make_float2(C1b.x, C1b.y);
                 const float2 rs = row_dot(tile + base + rowoff, C0, C1);
                 const float2 tt = cmul(rs, E01);
                 acc[u] = make_float2(tt.x * w01, tt.y * w01);
             }
             {   // rows 32..35 of the 8 samples: lane -> (sample ur, row 32 + rr)
                 const float* R = srec + (b * 8 + ur) * SRW;
-                const int base = __float_as_int(R[18]);
                 const float w01 = R[5] * R[6 + 2 + rr];
                 const float4 C0 = *reinterpret_cast<const float4*>(R + 12);
-                const float2 C1 = *reinterpret_cast<const float2*>(R + 16);
+                const float4 C1b = *reinterpret_cast<const float4*>(R + 16);
+                const int base = __float_as_int(C1b.z);
+                const float2 C1 = make_float2(C1b.x, C1b.y);
                 const float2 rs = row_dot(tile + base + rowoff_r, C0, C1);
                 const float2 tt = cmul(rs, E01r);
 #pragma unroll

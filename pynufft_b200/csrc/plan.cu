@@ -522,12 +522,14 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         // every column's samples (already in plane order) are cut into segments of at most COL_SEG samples; items
         // stay in column order (q2 fastest), so that columns whose halos overlap run close in time
         std::vector<WorkItem> cw;
+        int col_seg = COL_SEG;
+        if (const char* e = getenv("B200NUFFT_COL_SEG")) col_seg = std::max(16, atoi(e));    // tuning knob
         const long long tail_from = M - M / 8;        // the last eighth of the samples is cut four times finer
         for (int col = 0; col < col_ncol; ++col) {
             const int b = h_cbin[(size_t)col * g.K[0]], e = h_cbin[(size_t)(col + 1) * g.K[0]];
             const int n = e - b;
             if (n <= 0) continue;
-            const int seg = (long long)b >= tail_from ? COL_SEG / 4 : COL_SEG;
+            const int seg = (long long)b >= tail_from ? col_seg / 4 : col_seg;
             const int nseg = (n + seg - 1) / seg;
             for (int sgi = 0; sgi < nseg; ++sgi) {
                 const int sb = b + (int)((long long)n * sgi / nseg), se = b + (int)((long long)n * (sgi + 1) / nseg);

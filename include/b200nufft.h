@@ -205,6 +205,12 @@ int b200nufft_plan_get_col_perm(b200nufft_plan_t plan, int32_t* perm, int32_t* t
  * returns the TRUE grid (one extra pass); gridding_modulated leaves it modulated (iff gridding_is_modulated) for
  * ifft_crop_modulated, whose inverse FFT passes undo the modulation for free.  adjoint / selfadjoint use the pair. */
 int b200nufft_gridding_is_modulated(b200nufft_plan_t plan);
+/* k-space solvers (linalg/solve_device.py:351-461) may iterate on modulated vectors, G' = D G D^H with D diagonal and
+ * unitary has the same CG scalars: kspace_modulated(plan) == 1 means gridding_modulated, interp_modulated (the tiled
+ * gather reading the modulated grid directly) and ifft_crop_modulated all agree on that form; saves one pass over the
+ * grid per application of G = interp^H interp.                                                                 */
+int b200nufft_kspace_modulated(b200nufft_plan_t plan);
+int b200nufft_interp_modulated(b200nufft_plan_t plan, const b200_c64* grid, b200_c64* y, int nb, void* stream);
 int b200nufft_gridding_modulated(b200nufft_plan_t plan, const b200_c64* y, b200_c64* grid, int nb, void* stream);
 int b200nufft_ifft_crop_modulated(b200nufft_plan_t plan, b200_c64* grid, b200_c64* x, int nb, int mode, int combine,
                                   const b200_c64* sens, void* stream);

@@ -178,7 +178,8 @@ static inline bool use_bi(const b200nufft_plan_s* p, int nb) {
 }
 
 // tiled kernels (interp_tiled.cu / grid_tiled.cu); return B200_ERR_UNSUPPORTED if geometry does not fit
-int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
+// modulated: `grid` is the phase-modulated grid of the column-sweep gridding kernel (needs the plan's tables)
+int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool modulated);
 int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
 bool tiled_supported(const Geom& g);
 int ensure_scratch(b200nufft_plan_t p, int nb);
@@ -189,7 +190,12 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st);
 // the gridding output is phase-modulated iff the column-sweep kernel runs (gridding variant "auto")
 static inline bool gridding_modulated(const b200nufft_plan_s* p) { return p->has_col && p->gridding_variant == 0; }
-int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
+// the tiled gather can read that modulated grid directly (k-space solvers iterate on modulated vectors)
+static inline bool interp_takes_modulated(const b200nufft_plan_s* p) {
+    return p->has_col && p->d_mod && p->interp_variant != 1 && tiled_supported(p->g);
+}
+// grid_modulated: `grid` is phase-modulated (only legal when interp_takes_modulated(p))
+int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool grid_modulated);
 // modulated_ok: the caller accepts the phase-modulated grid (it hands it to ifft_crop_impl(..., modulated))
 int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool modulated_ok);
 // fft256.cu; `modulated`: the grid enters phase-modulated (col3d.cu)

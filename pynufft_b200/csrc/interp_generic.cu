@@ -101,11 +101,18 @@ k_gridding_generic(Geom g, const float* __restrict__ rec, long long M, const flo
     }
 }
 
-int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
+int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool grid_modulated) {
     if (p->M == 0) return B200_OK;
+    if (grid_modulated) {
+        if (!interp_takes_modulated(p)) {
+            b200_set_error("interp: this plan / variant cannot read a phase-modulated grid");
+            return B200_ERR_UNSUPPORTED;
+        }
+        return interp_tiled_launch(p, grid, y, nb, st, true);
+    }
     if (use_bi(p, nb)) return batch2d_interp(p, grid, y, nb, st);
     if (p->interp_variant != 1 && single2d_supported(p->g)) return single2d_interp(p, grid, y, nb, st);
-    if (p->interp_variant != 1 && tiled_supported(p->g)) return interp_tiled_launch(p, grid, y, nb, st);
+    if (p->interp_variant != 1 && tiled_supported(p->g)) return interp_tiled_launch(p, grid, y, nb, st, false);
     if (p->interp_variant == 2) {
         b200_set_error("interp: tiled variant requested but geometry unsupported");
         return B200_ERR_UNSUPPORTED;
@@ -142,7 +149,19 @@ int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cud
 extern "C" int b200nufft_interp(b200nufft_plan_t p, const b200_c64* grid, b200_c64* y, int nb, void* stream) {
     ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "interp: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
-    return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream));
+    return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream), false);
+}
+
+// interp on the phase-modulated grid b200nufft_gridding_modulated produces (k-space solvers); only when
+// b200nufft_kspace_modulated(plan) == 1
+extern "C" int b200nufft_interp_modulated(b200nufft_plan_t p, const b200_c64* grid, b200_c64* y, int nb, void* stream) {
+    ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "interp: bad arguments");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream), true);
+}
+// 1 if interp_modulated / gridding_modulated / ifft_crop_modulated all work on the phase-modulated grid
+extern "C" int b200nufft_kspace_modulated(b200nufft_plan_t p) {
+    return (p && gridding_modulated(p) && interp_takes_modulated(p)) ? 1 : 0;
 }
 
 extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {

@@ -17,6 +17,11 @@
 //    (4 lanes per sample); the 8 partial sums are reduced with a transposed butterfly
 //    (18 shuffles per 8 samples instead of 80) and scattered to y through the sort permutation.
 // No atomics, no global traffic inside the loop besides the y store.
+//
+// MOD = true: the kernel reads the phase-modulated grid G'[g] = G[g] * prod_d e^{i s_d g_d} that the column-sweep
+// gridding kernel produces (col3d.cu), so that k-space solvers can iterate on modulated vectors without converting.
+// The staged box then only needs the wrap signs (-1)^(N-1) of neighbours that wrap around the periodic grid, every
+// interpolation weight is real, and the sample's phase becomes P * prod_d e^{i s_d (1 - k_d)} (k_d = first neighbour).
 #include "common.cuh"
 
 namespace {
@@ -87,10 +92,16 @@ __device__ __forceinline__ int wrap2(int i, int K) {   // i in [0, 3K)
     i -= (i >= K) ? K : 0;
     return i;
 }
+__device__ __forceinline__ int wrap2s(int i, int K, float sg, float& sign) {   // same; sign *= sg per wrap
+    if (i >= K) { i -= K; sign *= sg; }
+    if (i >= K) { i -= K; sign *= sg; }
+    return i;
+}
 
+template <bool MOD>
 __global__ void __launch_bounds__(NTHREADS, 3)
 k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restrict__ rec,
-               const float2* __restrict__ grid, float2* __restrict__ y, int nb) {
+               const float2* __restrict__ grid, float2* __restrict__ y, int nb, const float2* __restrict__ mod) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* tile = reinterpret_cast<float2*>(smem_raw);
     float* srec = reinterpret_cast<float*>(smem_raw + TILE_ELEMS * sizeof(float2));
@@ -122,15 +133,21 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
         const int K0 = g.K[0], K1 = g.K[1], K2 = g.K[2];
         const int KK = K1 * K2;
         const bool act = lane < BOX;
-        const int i2 = wrap2(T2 + (act ? lane : 0), K2);
+        // MOD: the staged values only take the wrap signs (-1)^(N-1) per wrapped dimension
+        const float sg0 = ((g.N[0] - 1) & 1) ? -1.f : 1.f, sg1 = ((g.N[1] - 1) & 1) ? -1.f : 1.f,
+                    sg2 = ((g.N[2] - 1) & 1) ? -1.f : 1.f;
+        float s2 = 1.f;
+        const int i2 = wrap2s(T2 + (act ? lane : 0), K2, sg2, s2);
         const float2 F = g.Fl[act ? lane : 0];
         constexpr int RQ = (BOX + NWARPS - 1) / NWARPS;   // 3
         int roff[RQ], soff[RQ];
+        float rsg[RQ];
 #pragma unroll
         for (int q = 0; q < RQ; ++q) {
             const int r = warp + NWARPS * q;
             const bool ok = act && r < BOX;
-            roff[q] = ok ? wrap2(T1 + (r < BOX ? r : 0), K1) * K2 + i2 : -1;
+            rsg[q] = s2;
+            roff[q] = ok ? wrap2s(T1 + (r < BOX ? r : 0), K1, sg1, rsg[q]) * K2 + i2 : -1;
             soff[q] = r * RP + lane;
         }
         constexpr int PU = 4;                             // planes per batch -> 12 loads in flight per lane
@@ -149,9 +166,16 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
 #pragma unroll
             for (int pp = 0; pp < PU; ++pp) {
                 if (p0 + pp < NPL) {
+                    float sp = 1.f;
+                    if (MOD) wrap2s(T0 + p0 + pp, K0, sg0, sp);
 #pragma unroll
-                    for (int q = 0; q < RQ; ++q)
-                        if (roff[q] >= 0) tile[(p0 + pp) * PP + soff[q]] = cmul(v[pp][q], F);
+                    for (int q = 0; q < RQ; ++q) {
+                        if (roff[q] >= 0) {
+                            const float f = sp * rsg[q];
+                            tile[(p0 + pp) * PP + soff[q]] =
+                                MOD ? make_float2(v[pp][q].x * f, v[pp][q].y * f) : cmul(v[pp][q], F);
+                        }
+                    }
                 }
             }
         }
@@ -160,10 +184,10 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
     // ---- per-lane constants ----
     const int j0l = lane / 6 > 5 ? 5 : lane / 6, j1l = lane % 6;      // rows 0..31
     const int rowoff = j0l * PP + j1l * RP;
-    const float2 E01 = cmul(g.E[0][j0l], g.E[1][j1l]);
+    const float2 E01 = MOD ? make_float2(1.f, 0.f) : cmul(g.E[0][j0l], g.E[1][j1l]);
     const int rr = lane & 3;                                           // rows 32..35 = (5, 2+rr)
     const int rowoff_r = 5 * PP + (2 + rr) * RP;
-    const float2 E01r = cmul(g.E[0][5], g.E[1][2 + rr]);
+    const float2 E01r = MOD ? make_float2(1.f, 0.f) : cmul(g.E[0][5], g.E[1][2 + rr]);
     const int ur = lane >> 2;
 
     for (int sb = wi.begin; sb < wi.end; sb += SUBCHUNK) {
@@ -185,7 +209,14 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
                 const float4 v5 = *reinterpret_cast<const float4*>(R + 20);
                 const int ks0 = __float_as_int(v5.x), ks1 = __float_as_int(v5.y), ks2 = __float_as_int(v5.z);
                 const int base = (ks0 - T0) * PP + (ks1 - T1) * RP + (ks2 - T2);
-                const float2 Pp = cmul(Pr, g.Gl[ks2 - T2]);
+                float2 Pp;
+                if (MOD) {          // P * prod_d e^{i s_d} conj(m_d[k_d]),  m_d[k] = e^{i s_d k}
+                    const float2 e = cmul(cmul(g.E[0][0], g.E[1][0]), g.E[2][0]);
+                    const float2 m = cmul(cmul(__ldg(mod + ks0), __ldg(mod + g.K[0] + ks1)), __ldg(mod + g.K[0] + g.K[1] + ks2));
+                    Pp = cmul(Pr, cmulc(m, e));
+                } else {
+                    Pp = cmul(Pr, g.Gl[ks2 - T2]);
+                }
                 *reinterpret_cast<float2*>(R + 18) = make_float2(__int_as_float(base), v5.w);
                 *reinterpret_cast<float2*>(R + 20) = Pp;
             } else {
@@ -281,14 +312,22 @@ bool tiled_supported(const Geom& g) {
     return true;
 }
 
-int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
+int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool modulated) {
     if (!p->attr_interp) {      // once per plan (the attribute is per device, plans are per device)
-        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         p->attr_interp = true;
+    }
+    if (modulated && !p->d_mod) {
+        b200_set_error("interp: modulated grid requested but the plan has no modulation tables");
+        return B200_ERR_UNSUPPORTED;
     }
     if (p->n_work == 0) return B200_OK;
     dim3 gr(p->n_work, nb);
-    k_interp_tiled<<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_rec, grid, y, nb);
+    if (modulated)
+        k_interp_tiled<true><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_rec, grid, y, nb, p->d_mod);
+    else
+        k_interp_tiled<false><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_rec, grid, y, nb, nullptr);
     LAUNCH_CHECK();
     return B200_OK;
 }

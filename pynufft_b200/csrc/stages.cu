@@ -359,7 +359,7 @@ static int forward_impl(b200nufft_plan_t p, const float2* x, int x_single, const
     rc = b200nufft_pad_fft(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
                            x_single, reinterpret_cast<const b200_c64*>(sens), stream);
     if (rc) return rc;
-    return interp_impl(p, p->d_grid, y, nb, as_stream(stream));
+    return interp_impl(p, p->d_grid, y, nb, as_stream(stream), false);
 }
 
 static int adjoint_impl(b200nufft_plan_t p, const float2* y, float2* x, int nb, int combine, const float2* sens,

@@ -231,20 +231,31 @@ class NUFFT:
         _lib.check(self._lib.b200nufft_pad_fft(self._plan, _ptr(xx), _ptr(store), nb, 0, 0, None, _stream()))
         return view
 
-    def _k2y_device(self, k):
+    def _k2y_device(self, k, modulated=False):
+        """modulated: k is a phase-modulated k-space vector (only when _kspace_modulated())."""
         self._require_plan()
         store, nb, batched = self._grid_storage(k)
         y = torch.empty((self.M, nb) if batched else (self.M,), dtype=torch.complex64, device=self.device)
-        _lib.check(self._lib.b200nufft_interp(self._plan, _ptr(store), _ptr(y), nb, _stream()))
+        fn = self._lib.b200nufft_interp_modulated if modulated else self._lib.b200nufft_interp
+        _lib.check(fn(self._plan, _ptr(store), _ptr(y), nb, _stream()))
         return y
 
-    def _y2k_device(self, y):
+    def _y2k_device(self, y, modulated=False):
+        """modulated: leave the grid phase-modulated (only when _kspace_modulated())."""
         self._require_plan()
         y = self._check_dev(y, (self.M,), 'y')
         nb = self._nb_of(y, 1, 'y')
         view, store = self._new_grid(nb, y.dim() == 2)
-        _lib.check(self._lib.b200nufft_gridding(self._plan, _ptr(y), _ptr(store), nb, _stream()))
+        fn = self._lib.b200nufft_gridding_modulated if modulated else self._lib.b200nufft_gridding
+        _lib.check(fn(self._plan, _ptr(y), _ptr(store), nb, _stream()))
         return view
+
+    def _kspace_modulated(self):
+        """True when gridding, interp and the inverse FFT passes can all work on the phase-modulated grid of the
+        column-sweep gridding kernel (csrc/col3d.cu): k-space solvers then iterate on modulated vectors
+        (G' = D G D^H with D diagonal and unitary has the same CG scalars) and skip one grid pass per G."""
+        self._require_plan()
+        return int(self._lib.b200nufft_kspace_modulated(self._plan)) == 1
 
     def _k2xx_device(self, k):
         """Inverse FFT (in place on k when k is a coil-major view, like the reference's in-place FFT) + crop."""

@@ -92,19 +92,21 @@ def cg(nufft, gy, maxiter=30, group=None):
     if group is not None:
         import torch.distributed as dist
         allreduce = lambda t: dist.all_reduce(t, group=group)
-    bview = nufft._y2k_device(gy)
+    mod = nufft._kspace_modulated()      # iterate on phase-modulated k-space vectors where the kernels allow it
+    bview = nufft._y2k_device(gy, modulated=mod)
     batched = bview.dim() == nufft.ndims + 1
     nb = int(bview.shape[-1]) if batched else 1
     store = lambda view: nufft._grid_storage(view)[0]          # contiguous storage in the library layout (no copy)
     view = lambda flat: nufft._view_of(flat, nb, batched)
 
     def G(flat):
-        return store(nufft._y2k_device(nufft._k2y_device(view(flat))))
+        return store(nufft._y2k_device(nufft._k2y_device(view(flat), modulated=mod), modulated=mod))
 
     xs = cg_kspace(G, store(bview), maxiter, CudaVectorOps(L), allreduce)
     # inverse FFT, crop, divide by sn  (solve_device.py:463-480)
     x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=nufft.device)
-    _lib.check(L.b200nufft_ifft_crop(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
+    crop = L.b200nufft_ifft_crop_modulated if mod else L.b200nufft_ifft_crop
+    _lib.check(crop(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
     return x2
 
 

@@ -252,25 +252,28 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- e2e: host API, pinned host buffers, H2D + D2H of every step inside the timed region ----
     # A step = forward of a host image + adjoint of a host data vector, each delivered back to the host.  The host API
-    # is used in its pipelined form (NUFFT.forward/adjoint(..., slot=s) + wait): two steps are in flight, so the copies of
-    # one step overlap the kernels of its neighbours; every step still moves all of its inputs and outputs over PCIe.
+    # is used in its pipelined form (NUFFT.forward/adjoint(..., slot=s) + wait): NS steps are in flight, so the copy-in,
+    # the kernels and the copy-out of neighbouring steps overlap; every step still moves all of its inputs and outputs
+    # over PCIe.
     def pinned(shape):
         return torch.empty(shape, dtype=torch.complex64).pin_memory()
-    x_hosts = [x_host, pinned(ND)]
-    x_hosts[1].copy_(x_host)
-    y_in = [pinned((M,)), pinned((M,))]
-    y_out = [pinned((M,)), pinned((M,))]
-    xa_out = [pinned(ND), pinned(ND)]
+    NS = 3                                                       # steps in flight (staging slots used)
+    x_hosts = [x_host] + [pinned(ND) for _ in range(NS - 1)]
+    y_in = [pinned((M,)) for _ in range(NS)]
+    y_out = [pinned((M,)) for _ in range(NS)]
+    xa_out = [pinned(ND) for _ in range(NS)]
     A.forward(x_hosts[0].numpy(), out=y_in[0].numpy())          # realistic adjoint input: a forward result
-    y_in[1].copy_(y_in[0])
+    for s_ in range(1, NS):
+        x_hosts[s_].copy_(x_host)
+        y_in[s_].copy_(y_in[0])
     # coil-sharded many2one through the host boundary (N > 1): H2D y on a copy-in stream, adjoint, ONE asynchronous
     # all-reduce on the device, D2H on a copy-out stream; the same two-slot pipeline as the single-GPU host API
-    y_devs = [torch.empty((M,), dtype=torch.complex64, device=dev) for _ in range(2)]
+    y_devs = [torch.empty((M,), dtype=torch.complex64, device=dev) for _ in range(NS)]
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_comp = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    keep = [None, None]
+    ev_in = [torch.cuda.Event() for _ in range(NS)]
+    ev_comp = [torch.cuda.Event() for _ in range(NS)]
+    ev_out = [torch.cuda.Event() for _ in range(NS)]
+    keep = [None] * NS
 
     def dist_adjoint(s):
         cur = torch.cuda.current_stream()
@@ -291,8 +294,8 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_run(iters):
         for i in range(iters):
-            s = i & 1
-            if i >= 2:
+            s = i % NS
+            if i >= NS:
                 A.wait('forward', s)
                 if dist is None:
                     A.wait('adjoint', s)
@@ -303,14 +306,14 @@ def run_ours(args, rank, world, local_rank):
                 A.adjoint(y_in[s].numpy(), out=xa_out[s].numpy(), slot=s)
             else:
                 dist_adjoint(s)
-        for s in (0, 1):
+        for s in range(NS):
             A.wait('forward', s)
             if dist is None:
                 A.wait('adjoint', s)
             else:
                 ev_out[s].synchronize()
-    e2e_iters = max(4, min(args.steps, 50))
-    e2e_run(4)
+    e2e_iters = max(2 * NS, min(args.steps, 60))
+    e2e_run(2 * NS)
     ms_e2e = timed(lambda: e2e_run(e2e_iters), 1, 0)
     e2e_value = world * e2e_iters / (ms_e2e * 1e-3)
     h2d = x_host.numel() * 8 + y_in[0].numel() * 8
@@ -375,7 +378,7 @@ def run_ours(args, rank, world, local_rank):
                        'plan_seconds': plan_s, 'plan_bytes': int(lib.b200nufft_plan_bytes(A._plan))},
             'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': ms_e2e / e2e_iters, 'mode': 'pipelined host API, 2 steps in flight',
+                    'ms_per_step': ms_e2e / e2e_iters, 'mode': 'pipelined host API, %d steps in flight' % NS,
                     'blocking_ms_per_step': (ms_blk / blk_iters) if ms_blk else None},
             'gpu_launches': int(launches),
             'roofline': roofline,

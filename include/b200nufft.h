@@ -32,6 +32,7 @@ extern "C" {
 typedef struct { float re, im; } b200_c64;
 typedef struct b200nufft_plan_s* b200nufft_plan_t;
 
+#define B200NUFFT_HOST_SLOTS 4
 #define B200NUFFT_MAX_DIM 3
 #define B200NUFFT_MAX_J 16
 #define B200NUFFT_MAX_L 32
@@ -141,8 +142,8 @@ int b200nufft_forward_host(b200nufft_plan_t plan, const b200_c64* x_host, b200_c
 int b200nufft_adjoint_host(b200nufft_plan_t plan, const b200_c64* y_host, b200_c64* x_host,
                            int nb, void* stream);
 /* Pipelined variants for streams of host arrays: the H2D copy, the operator (on `stream`) and the D2H copy of
- * successive calls overlap (two copy streams inside the plan, chained by events); `slot` (0 or 1) selects one of two
- * staging buffers per direction.  Nothing blocks the host: call host_wait(op, slot) (op 0 forward, 1 adjoint) before
+ * successive calls overlap (two copy streams inside the plan, chained by events); `slot` (0 .. B200NUFFT_HOST_SLOTS-1)
+ * selects one of the staging buffers per direction (three calls in flight keep all three stages busy).  Nothing blocks the host: call host_wait(op, slot) (op 0 forward, 1 adjoint) before
  * reading the output of, or reusing the host buffers handed to, the last call on that (op, slot).  Host buffers must
  * be pinned for the copies to overlap.  */
 int b200nufft_forward_host_async(b200nufft_plan_t plan, const b200_c64* x_host, b200_c64* y_host, int nb, int slot,

@@ -149,10 +149,11 @@ struct b200nufft_plan_s {
     int io_nb = 0;
     // pipelined host entry points (stages.cu): copy streams, per-(direction, slot) staging buffers and events
     struct HostPipe {
+        static constexpr int NSLOT = B200NUFFT_HOST_SLOTS;
         cudaStream_t s_in = nullptr, s_out = nullptr;
-        float2* d_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};     // [0 forward | 1 adjoint][slot]
-        float2* d_out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-        cudaEvent_t ev_in[2][2], ev_comp[2][2], ev_out[2][2];
+        float2* d_in[2][NSLOT] = {};      // [0 forward | 1 adjoint][slot]
+        float2* d_out[2][NSLOT] = {};
+        cudaEvent_t ev_in[2][NSLOT], ev_comp[2][NSLOT], ev_out[2][NSLOT];
         int nb = 0;
         bool ready = false;
     } pipe;

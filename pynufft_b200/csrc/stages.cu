@@ -444,11 +444,13 @@ extern "C" int b200nufft_adjoint_host(b200nufft_plan_t p, const b200_c64* y_host
 // ---- pipelined host entry points ------------------------------------------------------------------------------
 // forward_host / adjoint_host above serialise copy-in, compute and copy-out.  The *_host_async pair overlaps them
 // across calls: H2D on a copy-in stream, the operator on the caller's stream, D2H on a copy-out stream, chained by
-// events, with two staging slots per direction; nothing blocks the host until b200nufft_host_wait(op, slot).
+// events, with B200NUFFT_HOST_SLOTS staging slots per direction (copy-in, operator and copy-out of three consecutive
+// calls can be in progress at once); nothing blocks the host until b200nufft_host_wait(op, slot).
 void host_pipe_destroy(b200nufft_plan_t p) {
     b200nufft_plan_s::HostPipe& h = p->pipe;
+    constexpr int NS = b200nufft_plan_s::HostPipe::NSLOT;
     for (int o = 0; o < 2; ++o)
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NS; ++s) {
             cudaFree(h.d_in[o][s]);
             cudaFree(h.d_out[o][s]);
             h.d_in[o][s] = h.d_out[o][s] = nullptr;
@@ -468,11 +470,12 @@ void host_pipe_destroy(b200nufft_plan_t p) {
 
 static int ensure_pipe(b200nufft_plan_t p, int nb) {
     b200nufft_plan_s::HostPipe& h = p->pipe;
+    constexpr int NS = b200nufft_plan_s::HostPipe::NSLOT;
     if (!h.ready) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h.s_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h.s_out, cudaStreamNonBlocking));
         for (int o = 0; o < 2; ++o)
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NS; ++s) {
                 CUDA_TRY(cudaEventCreateWithFlags(&h.ev_in[o][s], cudaEventDisableTiming));
                 CUDA_TRY(cudaEventCreateWithFlags(&h.ev_comp[o][s], cudaEventDisableTiming));
                 CUDA_TRY(cudaEventCreateWithFlags(&h.ev_out[o][s], cudaEventDisableTiming));
@@ -482,7 +485,7 @@ static int ensure_pipe(b200nufft_plan_t p, int nb) {
     if (h.nb >= nb) return B200_OK;
     CUDA_TRY(cudaDeviceSynchronize());                  // nothing may still use the old buffers
     const size_t xb = sizeof(float2) * p->g.Nprod * nb, yb = sizeof(float2) * std::max<long long>(p->M, 1) * nb;
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NS; ++s) {
         cudaFree(h.d_in[0][s]); cudaFree(h.d_out[0][s]); cudaFree(h.d_in[1][s]); cudaFree(h.d_out[1][s]);
         h.d_in[0][s] = h.d_out[0][s] = h.d_in[1][s] = h.d_out[1][s] = nullptr;
         h.nb = 0;
@@ -497,7 +500,7 @@ static int ensure_pipe(b200nufft_plan_t p, int nb) {
 
 static int host_async(b200nufft_plan_t p, int op, const b200_c64* in_host, b200_c64* out_host, int nb, int slot,
                       void* stream) {
-    ARG_CHECK(p && in_host && out_host && nb >= 1 && (slot == 0 || slot == 1), "host_async: bad arguments");
+    ARG_CHECK(p && in_host && out_host && nb >= 1 && slot >= 0 && slot < B200NUFFT_HOST_SLOTS, "host_async: bad arguments");
     CUDA_TRY(cudaSetDevice(p->device));
     int rc = ensure_pipe(p, nb);
     if (rc) return rc;
@@ -534,7 +537,7 @@ extern "C" int b200nufft_adjoint_host_async(b200nufft_plan_t p, const b200_c64* 
     return host_async(p, 1, y_host, x_host, nb, slot, stream);
 }
 extern "C" int b200nufft_host_wait(b200nufft_plan_t p, int op, int slot) {
-    ARG_CHECK(p && (op == 0 || op == 1) && (slot == 0 || slot == 1), "host_wait: bad arguments");
+    ARG_CHECK(p && (op == 0 || op == 1) && slot >= 0 && slot < B200NUFFT_HOST_SLOTS, "host_wait: bad arguments");
     if (!p->pipe.ready) return B200_OK;
     CUDA_TRY(cudaSetDevice(p->device));
     CUDA_TRY(cudaEventSynchronize(p->pipe.ev_out[op][slot]));

@@ -384,9 +384,10 @@ class NUFFT:
     def forward(self, x, out=None, slot=None):
         """Host forward NUFFT (reference: _forward_host).  `out` may be a preallocated (pinned) array.
 
-        slot=None: blocking, like the reference.  slot=0/1: pipelined -- the call only enqueues H2D copy, operator
+        slot=None: blocking, like the reference.  slot=0..3: pipelined -- the call only enqueues H2D copy, operator
         and D2H copy (they overlap with the neighbouring calls' copies and kernels) and returns `out` immediately;
-        call wait('forward', slot) before reading it or reusing x / out.  Use pinned arrays and alternate the slots."""
+        call wait('forward', slot) before reading it or reusing x / out.  Use pinned arrays and cycle through three
+        slots to keep copy-in, kernels and copy-out busy at the same time."""
         self._require_plan()
         x = self._host_c64(x, self.Nd, 'x')
         nb = x.shape[-1] if x.ndim == self.ndims + 1 else 1

@@ -95,10 +95,17 @@ __device__ __forceinline__ int next_item(int* counter, int lane) {
     return __shfl_sync(0xffffffffu, it, 0);
 }
 
-// ys[c][i] = (conj(P''_i) * y[perm[i], c], 0, 0): 16-byte slots so that any sample range is TMA-aligned
+// Pre-pass of the scatter, one kernel: ys[c][i] = (conj(P''_i) * y[perm[i], c], 0, 0) (16-byte slots so that any sample
+// range is TMA-aligned), the grid zero-fill (the gather is latency-bound on the random reads of y and leaves the
+// bandwidth to the stores) and the reset of the persistent kernel's work counters.
 __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M, const float2* __restrict__ y,
-                                    float4* __restrict__ ys, int nb) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+                                    float4* __restrict__ ys, int nb, float4* __restrict__ grid4, long long n4,
+                                    int* __restrict__ counters) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long T = gridDim.x * (long long)blockDim.x;
+    if (i < nb) counters[i] = 0;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long j = i; j < n4; j += T) grid4[j] = z;
     if (i >= M) return;
     const float4 h = __ldg(side + i);                 // P''.re, P''.im, original index
     const int m = __float_as_int(h.z);
@@ -298,16 +305,6 @@ static ColGeom col_geom(const Geom& g) {
     return c;
 }
 
-// per-coil work counters of the persistent kernel (zeroed on the stream before every launch)
-static int col_counters(b200nufft_plan_t p, int nb, cudaStream_t st) {
-    if (p->ccount_nb < nb) {
-        if (p->d_ccount) { CUDA_TRY(cudaFree(p->d_ccount)); p->d_ccount = nullptr; p->ccount_nb = 0; }
-        CUDA_TRY(cudaMalloc(&p->d_ccount, sizeof(int) * nb));
-        p->ccount_nb = nb;
-    }
-    CUDA_TRY(cudaMemsetAsync(p->d_ccount, 0, sizeof(int) * nb, st));
-    return B200_OK;
-}
 // CTAs per coil of the persistent kernel: all SMs x 5 resident CTAs, shared between the coils of the launch
 static int col_ctas(b200nufft_plan_t p, int nb) {
     if (p->n_sm == 0) {
@@ -326,24 +323,15 @@ int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st) 
     return B200_OK;
 }
 
-// grid (zero on entry) receives the phase-modulated adjoint
+// grid receives the phase-modulated adjoint (it is zeroed here, by the pre-pass)
 int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st) {
     if (!p->attr_col) {
         CUDA_TRY(cudaFuncSetAttribute(k_gridding_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
         p->attr_col = true;
     }
-    // the grid is zeroed on a side stream while this stream pre-gathers the sorted data; the scatter waits for both
-    if (!p->s_side) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&p->s_side, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaEventRecord(p->ev_fork, st));          // everything that used the grid before is ordered first
-    CUDA_TRY(cudaStreamWaitEvent(p->s_side, p->ev_fork, 0));
-    CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, p->s_side));
-    CUDA_TRY(cudaEventRecord(p->ev_join, p->s_side));
+    const long long nel = p->g.Kprod * nb;
     if (p->n_cwork == 0) {
-        CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join, 0));
+        CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * nel, st));
         return B200_OK;
     }
     if (p->ys_nb < nb) {
@@ -351,14 +339,20 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
         CUDA_TRY(cudaMalloc(&p->d_ys, sizeof(float4) * p->M * nb));
         p->ys_nb = nb;
     }
+    if (p->ccount_nb < nb) {
+        if (p->d_ccount) { CUDA_TRY(cudaFree(p->d_ccount)); p->d_ccount = nullptr; p->ccount_nb = 0; }
+        CUDA_TRY(cudaMalloc(&p->d_ccount, sizeof(int) * nb));
+        p->ccount_nb = nb;
+    }
+    // float4 stores need a 16-byte aligned grid and an even element count; otherwise plain memset
+    const bool vec = (reinterpret_cast<uintptr_t>(grid) & 15) == 0 && (nel & 1) == 0;
+    if (!vec) CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * nel, st));
     {
         const int TB = 256;
-        k_gather_sorted_col<<<(unsigned)((p->M + TB - 1) / TB), TB, 0, st>>>(p->d_cside, p->M, y, p->d_ys, nb);
+        k_gather_sorted_col<<<(unsigned)((p->M + TB - 1) / TB), TB, 0, st>>>(
+            p->d_cside, p->M, y, p->d_ys, nb, reinterpret_cast<float4*>(grid), vec ? nel / 2 : 0, p->d_ccount);
         LAUNCH_CHECK();
     }
-    int rc = col_counters(p, nb, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join, 0));
     dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb)), nb);
     k_gridding_col<<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
                                                                  p->d_crec, p->d_ys, p->M, grid);

@@ -129,8 +129,6 @@ struct b200nufft_plan_s {
     float4* d_cside = nullptr;      // (M,) (P''.re, P''.im, original index, 0) in sweep order
     WorkItem* d_cwork = nullptr;    // (column, begin, end) segments of at most COL_SEG samples
     int n_cwork = 0;
-    cudaStream_t s_side = nullptr;  // side stream: the grid memset runs beside the sorted-data pre-gather
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int* d_ccount = nullptr;        // per-coil work counters of the persistent column kernels
     int ccount_nb = 0;
     int n_sm = 0;
@@ -186,7 +184,7 @@ bool tiled_supported(const Geom& g);
 int ensure_scratch(b200nufft_plan_t p, int nb);
 // col3d.cu: register-resident column-sweep gridding (3-D, J = 6); the grid it produces is phase-modulated
 bool col3d_supported(const Geom& g);
-// zeroes the grid itself (on a side stream, beside the pre-gather)
+// zeroes the grid itself (inside its pre-pass kernel)
 int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st);
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st);
 // the gridding output is phase-modulated iff the column-sweep kernel runs (gridding variant "auto")

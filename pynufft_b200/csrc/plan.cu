@@ -555,11 +555,6 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     if (!p) return B200_OK;
     cudaSetDevice(p->device);
     host_pipe_destroy(p);
-    if (p->s_side) {
-        cudaStreamDestroy(p->s_side);
-        cudaEventDestroy(p->ev_fork);
-        cudaEventDestroy(p->ev_join);
-    }
     cudaFree(p->d_pc);
     cudaFree(p->d_om);
     cudaFree(p->d_perm);

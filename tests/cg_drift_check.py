@@ -1,3 +1,4 @@
+"""Diagnostic (run by hand on a GPU box): how far float32 CG drifts from the exact-arithmetic iterates on configuration 4."""
 import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import numpy, torch
 from oracle import nufft_oracle as orc

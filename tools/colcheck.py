@@ -1,10 +1,10 @@
-"""Quick GPU check of the column-sweep kernels against the oracle (small sizes) + timing at configuration 3."""
+"""Stage timings at configuration 3 for the default (tiled gather + column-sweep scatter) and the tiled-only variants.
+Parity of the same kernels lives in tests/test_gpu_parity.py (test_gridding_kernels_agree_3d)."""
 import sys, time
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy, torch
 import pynufft_b200
 from pynufft_b200 import _lib
-from oracle import nufft_oracle as orc
 
 def rel(a, b):
     a = numpy.asarray(a).ravel(); b = numpy.asarray(b).ravel()
@@ -12,27 +12,7 @@ def rel(a, b):
 
 dev = torch.device('cuda', 0)
 rng = numpy.random.default_rng(3)
-CASES = [] if (len(sys.argv) > 1 and sys.argv[1] == 'time') else [((32, 32, 32), (64, 64, 64), 20000), ((15, 20, 24), (30, 50, 48), 5000),
-                  ((8, 8, 8), (16, 16, 16), 300), ((33, 31, 32), (66, 62, 64), 30000), ((5, 4, 5), (6, 9, 10), 200)]
-for Nd, Kd, M in CASES:
-    Jd = (6, 6, 6)
-    om = rng.uniform(-numpy.pi, numpy.pi, (M, 3))
-    om[:7] = [[numpy.pi, numpy.pi, numpy.pi], [-numpy.pi, -numpy.pi, -numpy.pi], [0, 0, 0], [numpy.pi, 0, -numpy.pi],
-              [3.1, -3.1, 3.1], [-3.1, 3.1, -3.1], [0.001, -0.001, 3.14]]
-    A = pynufft_b200.NUFFT(dev); A.plan(om, Nd, Kd, Jd)
-    O = orc.NUFFT(); O.plan(om, Nd, Kd, Jd)
-    x = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
-    y = (rng.standard_normal(M) + 1j * rng.standard_normal(M)).astype(numpy.complex64)
-    cperm, ctile, csub = A._col_perm()
-    print(Nd, Kd, 'layout', A.layout(), ctile, csub, 'col perm ok', numpy.array_equal(cperm, orc.sort_permutation(O.p.k0, Kd, ctile, csub)))
-    for gv in (0, 2, 1):
-        if gv == 2 and min(Kd) < 16: continue
-        A.set_variant(0 if gv != 1 else 1, gv)
-        print('  gridding variant', gv, 'y2k', rel(A.y2k(y), O.y2k(y)), 'adj', rel(A.adjoint(y), O.adjoint(y)),
-              'selfadj', rel(A.selfadjoint(x), O.adjoint(O.forward(x).astype(numpy.complex64))))
-    A.release()
-
-if len(sys.argv) > 1:
+if True:
     # timing at configuration 3
     lib = _lib.load()
     import ctypes

@@ -80,6 +80,18 @@ for kern, short in (('k_interp_tiled', 'interp'), ('k_gridding_col', 'gridding')
     for x in sorted(data, key=lambda x: -int(x[isamp]))[:10]:
         out.append('| %.1f | %s | `%s` |' % (100 * int(x[isamp]) / tot, x[iex], x[isrc].strip()[:70]))
     out.append('')
+# the gridding STAGE bench.py times = pre-pass (zero-fill + sorted-data gather) + scatter: add the pre-pass traffic
+rows = run('raw', 'k_gather_sorted_col')
+if len(rows) >= 3 and 'gridding' in traffic:
+    hdr, units, r = rows[0], rows[1], rows[2]
+    def _b(h):
+        u = units[hdr.index(h)].lower()
+        return float(r[hdr.index(h)].replace(',', '')) * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}[u]
+    pre = _b('dram__bytes_read.sum') + _b('dram__bytes_write.sum')
+    traffic['gridding_scatter_kernel'] = traffic['gridding']
+    traffic['gridding_prepass_kernel'] = pre
+    traffic['gridding'] = traffic['gridding'] + pre
+    out.append('Gridding stage as timed by bench.py (pre-pass + scatter): DRAM traffic %.1f MB (pre-pass %.1f MB).\n' % (traffic['gridding'] / 1e6, pre / 1e6))
 os.makedirs(os.path.join(root, 'profiles'), exist_ok=True)
 open(os.path.join(root, 'profiles', '%s_ncu_summary.md' % tag), 'w').write('# ncu summary %s (B200, configuration 3)\n\n' % tag + '\n'.join(out) + '\n')
 json.dump(traffic, open(os.path.join(root, 'profiles', 'traffic.json'), 'w'))

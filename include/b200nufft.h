@@ -189,7 +189,8 @@ int b200nufft_tv_bregman(b200_c64* AHyk, const b200_c64* zf, const b200_c64* AHy
                          void* stream);
 
 /* ---- tuning / introspection ---------------------------------------------------------------- */
-/* kernel variant selection: interp/gridding "auto" (0), "generic" (1), "tiled" (2) */
+/* kernel variant selection: interp/gridding "auto" (0), "generic" (1), "tiled" (2); interp only: "column sweep" (3,
+ * the register-resident gather of csrc/col3d.cu on the phase-modulated grid; 3-D, Jd = 6^3, Kd[0] >= 10) */
 int b200nufft_set_variant(b200nufft_plan_t plan, int interp_variant, int gridding_variant);
 /* Column-sweep gridding (csrc/col3d.cu).  Plans for 3-D, Jd = 6^3 keep, next to the tile-sorted samples, a second
  * copy sorted by (4 x 5 column of first-neighbour cells, first plane) for the register-resident scatter kernel.
@@ -215,6 +216,11 @@ int b200nufft_interp_modulated(b200nufft_plan_t plan, const b200_c64* grid, b200
 int b200nufft_gridding_modulated(b200nufft_plan_t plan, const b200_c64* y, b200_c64* grid, int nb, void* stream);
 int b200nufft_ifft_crop_modulated(b200nufft_plan_t plan, b200_c64* grid, b200_c64* x, int nb, int mode, int combine,
                                   const b200_c64* sens, void* stream);
+/* pad_fft that leaves the grid phase-modulated, the form interp_modulated reads (the forward FFT passes multiply their
+ * outputs by the modulation tables; cuFFT path: one extra pass).  forward / forward_one2many use the pair
+ * pad_fft_modulated -> interp_modulated (the column-sweep gather, csrc/col3d.cu) when kspace_modulated(plan) == 1.  */
+int b200nufft_pad_fft_modulated(b200nufft_plan_t plan, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
+                                int x_single, const b200_c64* sens, void* stream);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t b200nufft_launch_count(void);
 

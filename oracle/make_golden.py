@@ -216,8 +216,119 @@ def run_case(name, om, Nd, Kd, Jd, seed, solvers=False):
     print(name, 'M=%d' % M, '%.1f KB' % (os.path.getsize(path) / 1024))
 
 
+def kindx_digest(kindx):
+    """sha256 of the reference's uint32 index array (C order): pins the WHOLE array bit for bit in 64 characters."""
+    import hashlib
+    return hashlib.sha256(numpy.ascontiguousarray(kindx.astype(numpy.uint32)).tobytes()).hexdigest()
+
+
+def run_config1_full():
+    """BASELINE configs[0] at full size on the reference's own fixtures: om2D.npz (PROPELLER, M = 122 880) and the
+    256 x 256 phantom, Kd 512^2, Jd 6^2 (tests/test_init.py of the reference).  The index array is pinned by its
+    sha256; forward / adjoint are stored as complex64 (the tolerance is 1e-5)."""
+    om = numpy.load('/root/reference/src/data/om2D.npz')['arr_0']
+    x = numpy.load('/root/reference/src/data/phantom_256_256.npz')['arr_0'].astype(c64)
+    Nd, Kd, Jd = (256, 256), (512, 512), (6, 6)
+    A = pynufft.NUFFT()
+    A.plan(om, Nd, Kd, Jd)
+    st = pynufft.helper.plan(om, Nd, Kd, Jd, format='pELL')
+    y = A.forward(x)
+    y64 = y.astype(c64)
+    out = dict(om=om, Nd=numpy.array(Nd), Kd=numpy.array(Kd), Jd=numpy.array(Jd), x=x.real.astype(numpy.float32),
+               kindx_sha256=numpy.array(kindx_digest(st['pELL'].kindx)),
+               forward=y64, adjoint=A.adjoint(y64).astype(c64), selfadjoint=A.selfadjoint(x).astype(c64))
+    path = os.path.join(OUT, 'ref_c1_full.npz')
+    numpy.savez_compressed(path, **out)
+    print('ref_c1_full', 'M=%d' % om.shape[0], '%.1f KB' % (os.path.getsize(path) / 1024))
+
+
+def run_config3_subset(nsel=20000, nvox=40000):
+    """BASELINE configs[2] (3-D 128^3 / 256^3 / 6^3, om = default_rng(0).uniform(-pi, pi, (2M, 3))) through the
+    reference on a random subset of the samples: forward rows are independent and the adjoint is linear in y, so the
+    subset pins the full-size operator.  Stored: the subset, its forward values, its index digest, and the adjoint of a
+    data vector supported on the subset at `nvox` random voxels (the full 128^3 image would be 16.8 MB)."""
+    Nd, Kd, Jd = (128, 128, 128), (256, 256, 256), (6, 6, 6)
+    om = numpy.random.default_rng(0).uniform(-numpy.pi, numpy.pi, (2_000_000, 3))
+    rng = numpy.random.default_rng(1)
+    x = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(c64)
+    sel = numpy.sort(rng.choice(om.shape[0], nsel, replace=False))
+    ysub = (rng.standard_normal(nsel) + 1j * rng.standard_normal(nsel)).astype(c64)
+    vox = numpy.sort(rng.choice(int(numpy.prod(Nd)), nvox, replace=False))
+    A = pynufft.NUFFT()
+    A.plan(om[sel], Nd, Kd, Jd)
+    st = pynufft.helper.plan(om[sel], Nd, Kd, Jd, format='pELL')
+    adj = A.adjoint(ysub).astype(c64)
+    out = dict(Nd=numpy.array(Nd), Kd=numpy.array(Kd), Jd=numpy.array(Jd), sel=sel.astype(numpy.int32), ysub=ysub,
+               vox=vox.astype(numpy.int32), kindx_sha256=numpy.array(kindx_digest(st['pELL'].kindx)),
+               forward=A.forward(x).astype(c64), adjoint_vox=adj.ravel()[vox],
+               adjoint_norm=numpy.array(numpy.linalg.norm(adj)))
+    path = os.path.join(OUT, 'ref_c3_subset.npz')
+    numpy.savez_compressed(path, **out)
+    print('ref_c3_subset', 'M=%d of 2000000' % nsel, '%.1f KB' % (os.path.getsize(path) / 1024))
+
+
+def gaussian_coil_maps(Nd, B, seed=0):
+    rng = numpy.random.default_rng(seed)
+    grids = numpy.meshgrid(*[numpy.arange(n) for n in Nd], indexing='ij')
+    maps = numpy.zeros(Nd + (B,), dtype=c64)
+    for c in range(B):
+        ang = 2 * numpy.pi * c / B
+        ctr = [Nd[0] / 2 + 0.45 * Nd[0] * numpy.cos(ang), Nd[1] / 2 + 0.45 * Nd[1] * numpy.sin(ang)] + \
+              [n / 2 for n in Nd[2:]]
+        r2 = sum((g - c0) ** 2 for g, c0 in zip(grids, ctr))
+        maps[..., c] = numpy.exp(-r2 / (2 * (0.6 * Nd[0]) ** 2)) * numpy.exp(1j * rng.uniform(0, 2 * numpy.pi))
+    return maps
+
+
+def run_multicoil(name, om, Nd, Kd, Jd, B, seed):
+    """B > 1 through the reference: its NUFFT_cpu.forward_one2many / adjoint_many2one (linalg/nufft_cpu.py:177-203) are
+    single-coil objects (plan() forces batch = 1, :107-108), so they are looped over the coils with the coil's map as
+    `cpu_coil_profile`, and the images are averaged over the coils as x2s / cAggregate do
+    (linalg/nufft_hsa.py:628-656, re_subroutine.py:441-497) -- BASELINE.md section 3."""
+    from reference.linalg.nufft_cpu import NUFFT_cpu
+    rng = numpy.random.default_rng(seed)
+    sens = gaussian_coil_maps(Nd, B, seed)
+    s = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(c64)
+    M = om.shape[0]
+    A = NUFFT_cpu()
+    A.plan(om, Nd, Kd, Jd)
+    y = numpy.zeros((M, B), dtype=c64)
+    for c in range(B):
+        A.volume['cpu_coil_profile'] = sens[..., c]
+        y[:, c] = A.forward_one2many(s)
+    y_in = (rng.standard_normal((M, B)) + 1j * rng.standard_normal((M, B))).astype(c64)
+    imgs, imgs2 = [], []
+    for c in range(B):
+        A.volume['cpu_coil_profile'] = sens[..., c]
+        imgs.append(A.adjoint_many2one(y_in[:, c]))
+        imgs2.append(A.adjoint_many2one(y[:, c]))
+    # batched forward / adjoint without coil maps (Nd+(B,) <-> (M, B)), coil by coil
+    A.volume['cpu_coil_profile'] = numpy.ones(Nd)
+    xb = (rng.standard_normal(Nd + (B,)) + 1j * rng.standard_normal(Nd + (B,))).astype(c64)
+    fwd_b = numpy.stack([A.forward(numpy.ascontiguousarray(xb[..., c])) for c in range(B)], -1).astype(c64)
+    adj_b = numpy.stack([A.adjoint(numpy.ascontiguousarray(y_in[:, c])) for c in range(B)], -1).astype(c64)
+    out = dict(om=om, Nd=numpy.array(Nd), Kd=numpy.array(Kd), Jd=numpy.array(Jd), B=numpy.array(B), sens=sens, s=s,
+               y_in=y_in, xb=xb, forward_one2many=y, adjoint_many2one=numpy.mean(imgs, axis=0).astype(c64),
+               selfadjoint_one2many2one=numpy.mean(imgs2, axis=0).astype(c64), forward_batch=fwd_b, adjoint_batch=adj_b)
+    path = os.path.join(OUT, name + '.npz')
+    numpy.savez_compressed(path, **out)
+    print(name, 'M=%d B=%d' % (M, B), '%.1f KB' % (os.path.getsize(path) / 1024))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if 'big' in sys.argv[1:] or 'all' in sys.argv[1:]:
+        run_config1_full()
+        run_config3_subset()
+        rng = numpy.random.default_rng(77)
+        th = numpy.arange(24) * numpy.pi * (numpy.sqrt(5.0) - 1.0) / 2.0        # golden-angle radial, 24 spokes x 128
+        r = numpy.pi * (numpy.arange(128) - 64) / 64
+        om = numpy.stack([numpy.outer(numpy.cos(th), r), numpy.outer(numpy.sin(th), r)], -1).reshape(-1, 2)
+        run_multicoil('ref_2d_batch8', om, (64, 64), (128, 128), (6, 6), 8, 11)
+        run_multicoil('ref_3d_batch3', rng.uniform(-numpy.pi, numpy.pi, (2500, 3)), (16, 16, 16), (32, 32, 32),
+                      (6, 6, 6), 3, 12)
+        if 'all' not in sys.argv[1:]:
+            return
     om2d = numpy.load('/root/reference/src/data/om2D.npz')['arr_0']
     rng = numpy.random.default_rng(1234)
     # 2D, PROPELLER trajectory subsample of the reference fixture, K/N == 2 branch

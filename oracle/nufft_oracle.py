@@ -476,14 +476,23 @@ def laplacian_kernel(Kd):
 
 
 def solve_l1tvols(nufft, y, maxiter, rho):
-    """linalg/solve_device.py:74-275 (split-Bregman TV, device variant)."""
+    """linalg/solve_device.py:74-275 (split-Bregman TV, device variant).
+
+    Multi-coil data y (M, B) on a batch operator: the same iteration with the closures of the batched twin
+    (linalg/solve_hsa.py:275-476, AHA = nufft.selfadjoint, AH = nufft.adjoint at :282-287) acting between the ONE image
+    the solver carries (every work array has shape st['Nd'], :291-318) and the B coils, i.e.
+    AH = adjoint_many2one and AHA = selfadjoint_one2many2one (linalg/nufft_hsa.py:658-672, 747-769): TV-SENSE.
+    The sampling density |y2k(1_M)| and the xx2k / k2xx of the Ku = rhs solve stay single-image (:288, :366-375)."""
     c64 = numpy.complex64
+    multi = y.ndim == 2
+    AH = nufft.adjoint_many2one if multi else nufft.adjoint
+    AHA = nufft.selfadjoint_one2many2one if multi else nufft.selfadjoint
     mu = 1.0
     LMBD = rho * mu
     nd = nufft.ndims
     w = numpy.abs(nufft.y2k(numpy.ones((nufft.M,), dtype=c64)).astype(c64))   # :25-36
     uker = (mu * w - LMBD * laplacian_kernel(nufft.Kd)).astype(c64)
-    AHy = nufft.adjoint(y).astype(c64)
+    AHy = AH(y).astype(c64)
     z = numpy.zeros(nufft.Nd, dtype=c64)
     xkp1 = z.copy()
     AHyk = z.copy()
@@ -507,7 +516,7 @@ def solve_l1tvols(nufft, y, maxiter, rho):
         xkp1 = nufft.k2xx(k).astype(c64)
         for pp in range(nd):
             zz[pp] = D(xkp1, pp)
-        zf = (nufft.selfadjoint(xkp1).astype(c64) - AHy).astype(c64)
+        zf = (AHA(xkp1).astype(c64) - AHy).astype(c64)
         s_tmp = [(zz[pp] + bb[pp]).astype(c64) for pp in range(nd)]
         s = s_tmp[0].copy()
         for pp in range(1, nd):                                     # cHypot, re_subroutine.py:656-678

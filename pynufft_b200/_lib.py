@@ -59,6 +59,7 @@ SIGNATURES = {
     'b200nufft_interp_modulated': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_gridding_modulated': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_ifft_crop_modulated': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    'b200nufft_pad_fft_modulated': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     'b200nufft_launch_count': (_i64, []),
 }
 

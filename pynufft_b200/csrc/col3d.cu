@@ -1,29 +1,36 @@
-// Column-sweep gridding kernel for 3-D, J = 6: the register-resident replacement of pELL_spmvh_mCoil +
-// atomic_add_float2 (src/re_subroutine.py:527-596, 275-287).
+// Column-sweep interpolation (gather) and gridding (scatter) kernels for 3-D, J = 6: the register-resident replacement
+// of pELL_spmv_mCoil and pELL_spmvh_mCoil + atomic_add_float2 (src/re_subroutine.py:751-835, 527-596, 275-287).
 //
-// The shared-memory tiled kernel (grid_tiled.cu) is bound by the shared-memory pipe: every one of the 216 neighbours
-// of a sample is an LDS + STS.  Here the grid cells a warp works on live in REGISTERS:
+// The shared-memory tiled kernels (interp_tiled.cu, grid_tiled.cu) are bound by the shared-memory pipe: every one of the
+// 216 neighbours of a sample is an LDS (gather) or an LDS + STS (scatter).  Here the grid cells a warp works on live in
+// REGISTERS and the inner loop is packed FP32 math (FFMA2, two lanes of a complex number per instruction):
 //
 //  * a second copy of the samples is sorted by (column, first plane): a column is a 4 x 5 cross-section (dims 1, 2)
 //    of first-neighbour cells, swept along dim 0 in increasing plane order (key = column * K0 + first plane);
-//  * the footprint of a sample lies inside the 9 x 10 box of its column (4 + 5 rows, 5 + 5 columns) and covers, in
-//    dim 0, exactly one plane of every residue class mod 6.  Lane (g, c), g = 0..2, c = 0..9 (30 lanes), owns the
-//    box cells (rows g, g + 3, g + 6; column c) of the six planes of the current window [p0, p0 + 6): plane p sits in
-//    slot p mod 6, 18 complex accumulators per lane.  Samples arrive in plane order, so the window only slides
-//    forward; the planes it leaves are flushed by ALL lanes at once (warp-uniform, three 8-byte REDs per lane that
-//    cover three 80-byte row segments per instruction) and their slots are cleared;
-//  * the inner loop is branch-free and every weight is a plain register operand: the record holds the dim-0 weights
-//    already rotated to the slots, the dim-1 weights as a zero-padded table over the box rows and the dim-2 weights
-//    zero-padded over the box columns, so a sample is 8 FMUL + 36 FFMA per lane on static registers;
-//  * all weights are REAL: the grid this kernel produces is phase-modulated, G'[g] = G[g] * prod_d e^{i s_d g_d}
-//    (s_d = gamma_d (N_d - 1) / 2), which turns the reference's complex min-max coefficients
-//    u_j = c_j e^{i om N/2} e^{-i s (dk - j)} (helper.py:148-162, 606-618) into c_j times ONE phase per sample (folded
-//    into the pre-gathered data).  The modulation is undone for free by the inverse FFT passes (fft256.cu) or by
-//    k_demodulate below; neighbours that wrap around the periodic grid pick up the sign e^{i s K} = (-1)^(N-1);
-//  * sample records (128 B, precomputed at plan time in sweep order) and the pre-gathered data arrive by
-//    double-buffered TMA bulk copies; warps are persistent and fetch work items (segments of a column) from a
-//    per-coil counter.
+//  * the footprint of a sample lies inside the 9 x 10 box of its column (4 + 5 rows, 5 + 5 columns).  Lane (g, c),
+//    g = 0..2, c = 0..9 (30 lanes), owns the box cells (rows g, g + 3, g + 6; column c) of the planes of the current
+//    window [p, p + 6).  Samples arrive in plane order, so the window only slides forward, one plane at a time;
+//  * STATIC PLANE PHASES: the code is unrolled over the residue of the window's first plane (p mod 6 for the scatter,
+//    p mod 8 for the gather, whose register ring also holds the two planes that are still in flight), so that inside a
+//    phase every accumulator / ring slot is a fixed register and the sample's dim-0 weights c0[j] need no rotation.
+//    A phase = "take every sample whose first plane is p, then retire plane p" and falls through into the next one;
+//  * scatter: the retired plane is flushed by ALL lanes at once, three 8-byte REDs per lane that cover three 80-byte
+//    row segments per instruction, and its registers are cleared.  gather: the retired plane's registers receive
+//    plane p + 8 by three 8-byte loads per lane that are consumed two window moves later (the L2 latency is covered
+//    by the samples in between and by the other warps); the 30 partial sums of a sample go through a 16-sample
+//    shared-memory transpose;
+//  * a sample is 5 LDS + 22 packed FP32 instructions per lane: the record holds the dim-1 weights as a zero-padded
+//    table over the box rows and the dim-2 weights zero-padded over the box columns, all REAL, because the grid these
+//    kernels work on is phase-modulated, G'[g] = G[g] * prod_d e^{i s_d g_d} (s_d = gamma_d (N_d - 1) / 2), which turns
+//    the reference's complex min-max coefficients u_j = c_j e^{i om N/2} e^{-i s (dk - j)} (helper.py:148-162, 606-618)
+//    into c_j times ONE phase per sample.  Neighbours that wrap around the periodic grid pick up the sign
+//    e^{i s K} = (-1)^(N-1): folded into the record's weights at plan time (plan.cu k_col_records);
+//  * the modulation is applied / undone for free by the fused FFT passes (fft256.cu) or by k_modulate / k_demodulate;
+//  * sample records (128 B, precomputed at plan time in sweep order) and the scatter's pre-gathered data arrive by
+//    double-buffered TMA bulk copies; warps are persistent and fetch work items (segments of a column) from a per-coil
+//    counter.
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -39,16 +46,26 @@ constexpr int CRECW = COL_RECW;           // words per record: 32
 constexpr int CCH = 16;                   // samples per chunk
 constexpr int CWARPS = 4;                 // warps per CTA (each warp works on its own items)
 constexpr int REC_BYTES = CCH * CRECW * 4;            // 2048
-constexpr int YS_BYTES = CCH * 16;
-constexpr int GWARP_BYTES = 4736;                     // 2 * REC + 2 * YS + mbar, rounded to 128
+constexpr int YS_BYTES = 160;                         // up to 18 pre-gathered values (8 B) per chunk, 16-byte multiple
+constexpr int GWARP_BYTES = 4608;                     // scatter: 2 * REC + 2 * YS + dummy record + mbar, rounded to 128
+#ifndef COL_IRING
+#define COL_IRING 10
+#endif
+constexpr int IRING = COL_IRING;                      // gather: planes in the register ring (window 6 + in flight)
+static_assert(IRING == 8 || IRING == 10, "phase list below");
+constexpr int PBUF_PITCH = 33;                        // gather: partial sums pbuf[sample][lane], float2
+constexpr int PBUF_BYTES = CCH * PBUF_PITCH * 8;      // 4224
+constexpr int IWARP_BYTES = 8448;                     // gather: 2 * REC + PBUF + mbar, rounded to 128
 static_assert(CT1 == 4 && CT2 == 5 && CRECW == 32 && CROWS == 3 * CNR, "record layout below assumes 4 x 5 columns");
-static_assert(2 * REC_BYTES + 2 * YS_BYTES + 16 <= GWARP_BYTES, "per-warp shared memory");
+static_assert(2 * REC_BYTES + 2 * YS_BYTES + 128 + 16 <= GWARP_BYTES, "per-warp shared memory (scatter)");
+static_assert(2 * REC_BYTES + PBUF_BYTES + 16 <= IWARP_BYTES, "per-warp shared memory (gather)");
 
-// record words: [c1g[0..11] | c0rot[0..5] | p0 | p0 mod 6 | w10[0..9] | 0 0]   (plan.cu k_col_records)
+// record words: [c1g[0..11] | c0[0..5] | p0 | run | w10[0..9] | 0 0]   (plan.cu k_col_records)
 
 struct ColGeom {
     int K0, K1, K2, nq2;
-    float sg0, sg1, sg2;        // e^{i s_d K_d} = (-1)^(N_d - 1): factor of neighbours that wrap
+    int dbg;                    // experiments (B200NUFFT_COL_DBG): bit 0 = skip the REDs / plane loads
+    int pf_ahead;               // gather: planes between the register ring's newest plane and the L2 prefetch (0 = none)
     long long Kprod;
 };
 
@@ -77,6 +94,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// ---- packed FP32 (a complex number = one 64-bit register pair): FFMA2 / FMUL2 through the sm_100 intrinsics ----
+// bc2(a) = {a, a}: ptxas folds it into the scalar-broadcast operand form (FFMA2 Rd, Ra.F32, Rb.F32x2, Rc.F32x2)
+typedef float2 P2;      // packed (re, im) pair
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void ffma2_acc(float2& acc, float2 a, float2 b) { acc = __ffma2_rn(a, b, acc); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+
 __device__ __forceinline__ void red_v2(float2* addr, float2 a) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a.x), "f"(a.y) : "memory");
 }
@@ -95,37 +119,39 @@ __device__ __forceinline__ int next_item(int* counter, int lane) {
     return __shfl_sync(0xffffffffu, it, 0);
 }
 
-// Pre-pass of the scatter, one kernel: ys[c][i] = (conj(P''_i) * y[perm[i], c], 0, 0) (16-byte slots so that any sample
-// range is TMA-aligned), the grid zero-fill (the gather is latency-bound on the random reads of y and leaves the
-// bandwidth to the stores) and the reset of the persistent kernel's work counters.
-__global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M, const float2* __restrict__ y,
-                                    float4* __restrict__ ys, int nb, float4* __restrict__ grid4, long long n4,
-                                    int* __restrict__ counters) {
+// Pre-pass of the scatter, one kernel: ys[c][i] = conj(P''_i) * y[perm[i], c] (8-byte slots, coil stride Mpad), the grid
+// zero-fill (the gather is latency-bound on the random reads of y and leaves the bandwidth to the stores) and the reset
+// of the persistent kernel's work counters.
+__global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M, long long Mpad,
+                                    const float2* __restrict__ y, float2* __restrict__ ys, int nb,
+                                    float4* __restrict__ grid4, long long n4, int* __restrict__ counters) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long T = gridDim.x * (long long)blockDim.x;
-    if (i < nb) counters[i] = 0;
+    for (long long j = i; j < nb; j += T) counters[j] = 0;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long j = i; j < n4; j += T) grid4[j] = z;
-    if (i >= M) return;
-    const float4 h = __ldg(side + i);                 // P''.re, P''.im, original index
-    const int m = __float_as_int(h.z);
-    for (int c = 0; c < nb; ++c) {
-        const float2 v = cmulc(make_float2(h.x, h.y), y[(long long)m * nb + c]);
-        ys[(long long)c * M + i] = make_float4(v.x, v.y, 0.f, 0.f);
+    for (long long s = i; s < M; s += T) {
+        const float4 h = __ldg(side + s);               // P''.re, P''.im, original index
+        const int m = __float_as_int(h.z);
+        for (int c = 0; c < nb; ++c) ys[(long long)c * Mpad + s] = cmulc(make_float2(h.x, h.y), y[(long long)m * nb + c]);
     }
 }
 
-__global__ void __launch_bounds__(CWARPS * 32, 5)
+// ---------------------------------------------------------------------------------------------------------
+// gridding (scatter): produces the phase-modulated grid
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CWARPS * 32, 4)
 k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __restrict__ counter,
-               const float* __restrict__ rec, const float4* __restrict__ ys, long long M, float2* __restrict__ grid) {
+               const float* __restrict__ rec, const float2* __restrict__ ys, long long Mpad, float2* __restrict__ grid) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* ws = smem_raw + warp * GWARP_BYTES;
     unsigned char* ybuf = ws + 2 * REC_BYTES;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + 2 * YS_BYTES);
+    float* dummy = reinterpret_cast<float*>(ws + 2 * REC_BYTES + 2 * YS_BYTES);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + 2 * YS_BYTES + 128);
     const int c = blockIdx.y;
     float2* gc = grid + (long long)c * g.Kprod;
-    const float4* ysc = ys + (long long)c * M;
+    const float2* ysc = ys + (long long)c * Mpad;
     // lanes 30, 31 shadow lane 29's cells with the always-zero record word 30 as their column weight: their
     // accumulators stay exactly zero and their REDs add 0 to valid cells, so the flush needs no predicate
     const bool active = lane < 3 * CCOLS;
@@ -133,33 +159,29 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
     const int lc = active ? lane - CCOLS * lg : CCOLS - 1;   // box column
     const int lw = active ? lc : CCOLS;                 // word 20 + lw of the record: this lane's column weight
     const int KK = g.K1 * g.K2;
-    const unsigned sbit0 = g.sg0 < 0.f ? 0x80000000u : 0u, sbit1 = g.sg1 < 0.f ? 0x80000000u : 0u,
-                   sbit2 = g.sg2 < 0.f ? 0x80000000u : 0u;
     if (lane == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    // the record that ends every item: first plane = INT_MAX (the phases then only retire what is left)
+    dummy[lane] = lane == 18 ? __int_as_float(INT_MAX) : 0.f;
     __syncwarp();
     unsigned gk = 0;                                    // chunks consumed by this warp so far (mbarrier phases)
 
     for (int item = next_item(counter + c, lane); item < n_work; item = next_item(counter + c, lane)) {
         const WorkItem wi = work[item];
         const int q1 = wi.tile / g.nq2, q2 = wi.tile - q1 * g.nq2;
-        // this lane's three cells inside plane 0, and the sign bits of their wrap factors
+        // this lane's three cells inside plane 0
         float2* cell[CNR];
-        unsigned rbit[CNR];
         {
             int col = q2 * CT2 + lc;
-            unsigned cbit = 0u;
-            if (col >= g.K2) { col -= g.K2; cbit = sbit2; }
+            if (col >= g.K2) col -= g.K2;
 #pragma unroll
             for (int i = 0; i < CNR; ++i) {
                 int row = q1 * CT1 + lg + 3 * i;
-                unsigned b = cbit;
-                if (row >= g.K1) { row -= g.K1; b ^= sbit1; }
+                if (row >= g.K1) row -= g.K1;
                 cell[i] = gc + (row * g.K2 + col);
-                rbit[i] = b;
             }
         }
         const int nchunks = (wi.end - wi.begin + CCH - 1) / CCH;
@@ -167,110 +189,369 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
             const int s = wi.begin + k * CCH;
             const int ns = min(CCH, wi.end - s);
             const unsigned b = (gk + k) & 1;
-            mbar_expect(&mbar[b], (unsigned)(ns * (CRECW * 4 + 16)));
+            const int sa = s & ~1;                                     // 16-byte aligned start of the 8-byte data
+            const unsigned yb = (unsigned)(((ns + (s & 1) + 1) & ~1) * 8);
+            mbar_expect(&mbar[b], (unsigned)(ns * CRECW * 4) + yb);
             tma_bulk(ws + b * REC_BYTES, rec + (long long)s * CRECW, (unsigned)(ns * CRECW * 4), &mbar[b]);
-            tma_bulk(ybuf + b * YS_BYTES, ysc + s, (unsigned)(ns * 16), &mbar[b]);
+            tma_bulk(ybuf + b * YS_BYTES, ysc + sa, yb, &mbar[b]);
         };
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) issue(0);
 
-        float2 A[6][CNR];               // [plane slot][row]
+        P2 A[6][CNR];                  // [plane slot][row], packed (re, im)
 #pragma unroll
         for (int s = 0; s < 6; ++s)
 #pragma unroll
             for (int i = 0; i < CNR; ++i) A[s][i] = make_float2(0.f, 0.f);
-        int pbase = -1, slot = 0;       // first plane of the window and its slot (warp-uniform)
+        int kc = 0, u = 0, ns = 0;      // next chunk, sample inside the chunk, samples of the chunk
+        int K = 0;                      // phase = slot of the window's first plane
+        int p = 0, pw = 0, poff = 0;    // first plane of the window, the same wrapped into the grid, its element offset
+        int plim = 0, pnext = 0;        // last plane that holds contributions; first plane of the next sample
+        bool started = false;
+        const float* Rb = dummy;
+        const float2* Y = reinterpret_cast<const float2*>(dummy);
 
-        // plane p (slot s) leaves the window: add this lane's cells to the grid (vector REDs), clear the slot.
-        // The wrap factors are +-1: applied as sign-bit flips.
-#define COL_FLUSH_SLOT(SS)                                                                         \
-    case SS: {                                                                                     \
-        _Pragma("unroll") for (int i = 0; i < CNR; ++i) {                                          \
-            const unsigned fb = pbit ^ rbit[i];                                                    \
-            const float2 v = make_float2(__uint_as_float(__float_as_uint(A[SS][i].x) ^ fb),        \
-                                         __uint_as_float(__float_as_uint(A[SS][i].y) ^ fb));       \
-            red_v2(cell_at(cell[i], poff), v);                                                     \
-            A[SS][i] = make_float2(0.f, 0.f);                                                      \
-        }                                                                                          \
-    } break;
-        auto flush = [&](int s, int p) {
-            unsigned pbit = 0u;
-            if (p >= g.K0) { p -= g.K0; pbit = sbit0; }
-            const int poff = p * KK;                    // < prod(Kd) < 2^31
-            switch (s) {
-                COL_FLUSH_SLOT(0)
-                COL_FLUSH_SLOT(1)
-                COL_FLUSH_SLOT(2)
-                COL_FLUSH_SLOT(3)
-                COL_FLUSH_SLOT(4)
-                COL_FLUSH_SLOT(5)
-            }
-        };
-#undef COL_FLUSH_SLOT
-
-        for (int k = 0; k < nchunks; ++k) {
-            const int ns = min(CCH, wi.end - (wi.begin + k * CCH));
-            const unsigned b = (gk + k) & 1;
-            if (k + 1 < nchunks) {
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) issue(k + 1);
-            }
-            mbar_wait(&mbar[b], ((gk + k) >> 1) & 1);
-            const float* Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
-            const float4* Y = reinterpret_cast<const float4*>(ybuf + b * YS_BYTES);
-#pragma unroll 2
-            for (int u = 0; u < ns; ++u) {
-                const float* R = Rb + u * CRECW;
-                const float4 C1 = *reinterpret_cast<const float4*>(R + 4 * lg);       // c1 of rows lg, lg+3, lg+6
-                const float4 C0a = *reinterpret_cast<const float4*>(R + 12);          // c0rot[0..3]
-                const float4 C0b = *reinterpret_cast<const float4*>(R + 16);          // c0rot[4..5], p0, p0 mod 6
-                const float w = R[20 + lw];
-                const float2 yv = *reinterpret_cast<const float2*>(Y + u);            // conj(P'') * y
-                const int p0 = __float_as_int(C0b.z);
-                if (p0 != pbase) {                        // warp-uniform: the window moved
-                    if (pbase >= 0) {
-                        const int n = min(p0 - pbase, 6);
-                        int s = slot, p = pbase;
-                        for (int e = 0; e < n; ++e) {
-                            flush(s, p);
-                            s = (s == 5) ? 0 : s + 1;
-                            ++p;
-                        }
-                    }
-                    pbase = p0;
-                    slot = __float_as_int(C0b.w);
-                }
-                const float vx = w * yv.x, vy = w * yv.y;
-                const float c1v[CNR] = {C1.x, C1.y, C1.z};
-                const float c0v[6] = {C0a.x, C0a.y, C0a.z, C0a.w, C0b.x, C0b.y};
-#pragma unroll
-                for (int i = 0; i < CNR; ++i) {
-                    const float tx = c1v[i] * vx, ty = c1v[i] * vy;
-#pragma unroll
-                    for (int s = 0; s < 6; ++s) {
-                        A[s][i].x = fmaf(c0v[s], tx, A[s][i].x);
-                        A[s][i].y = fmaf(c0v[s], ty, A[s][i].y);
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        if (pbase >= 0) {
-            int s = slot, p = pbase;
-            for (int e = 0; e < 6; ++e) {
-                flush(s, p);
-                s = (s == 5) ? 0 : s + 1;
-                ++p;
-            }
-        }
-        gk += nchunks;
+#define COL_ACC(SL, I, CV, TV) ffma2_acc(A[SL][I], bc2(CV), TV);
+#define COL_ACC_ROW(KC, I, TV, C0a, C0b)    \
+    COL_ACC((KC + 0) % 6, I, C0a.x, TV)     \
+    COL_ACC((KC + 1) % 6, I, C0a.y, TV)     \
+    COL_ACC((KC + 2) % 6, I, C0a.z, TV)     \
+    COL_ACC((KC + 3) % 6, I, C0a.w, TV)     \
+    COL_ACC((KC + 4) % 6, I, C0b.x, TV)     \
+    COL_ACC((KC + 5) % 6, I, C0b.y, TV)
+        // the record of sample U of the chunk into register set X (reads past the chunk stay inside this warp's
+        // shared memory and are never used)
+#define COL_S_LOAD(X, U)                                                                           \
+    {                                                                                              \
+        const float* R = Rb + (U) * CRECW;                                                         \
+        X##C1 = *reinterpret_cast<const float4*>(R + 4 * lg);                                      \
+        X##C0a = *reinterpret_cast<const float4*>(R + 12);                                         \
+        X##C0b = *reinterpret_cast<const float2*>(R + 16);                                         \
+        X##w = R[20 + lw];                                                                         \
+        X##yv = *reinterpret_cast<const P2*>(Y + (U));                                            \
     }
+#define COL_S_BODY(KC, X)                                                                          \
+    {                                                                                              \
+        const P2 v = fmul2(bc2(X##w), X##yv);                                                     \
+        const P2 t0 = fmul2(bc2(X##C1.x), v), t1 = fmul2(bc2(X##C1.y), v), t2 = fmul2(bc2(X##C1.z), v); \
+        COL_ACC_ROW(KC, 0, t0, X##C0a, X##C0b)                                                     \
+        COL_ACC_ROW(KC, 1, t1, X##C0a, X##C0b)                                                     \
+        COL_ACC_ROW(KC, 2, t2, X##C0a, X##C0b)                                                     \
+    }
+        // phase KC: plane p sits in slot KC.  Take every sample whose first plane is p -- the record carries the length of
+        // the run of samples that share its (column, first plane), so this is a counted loop (two samples per trip, all
+        // loads ahead of the math) instead of a load -> compare -> branch chain per sample -- then retire plane p.
+#define COL_S_PHASE(KC)                                                                            \
+    case KC: {                                                                                     \
+        if (u == ns) { K = KC; goto chunk_done; }                                                  \
+        {                                                                                          \
+            const int2 pr = *reinterpret_cast<const int2*>(Rb + u * CRECW + 18);   /* p0, run */   \
+            pnext = pr.x;                                                                          \
+            if (pnext == p) {                                                                      \
+                int n = min(pr.y, ns - u);                                                         \
+                _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                                   \
+                    COL_S_LOAD(a, u)                                                               \
+                    COL_S_LOAD(b, u + 1)                                                           \
+                    COL_S_BODY(KC, a)                                                              \
+                    COL_S_BODY(KC, b)                                                              \
+                }                                                                                  \
+                if (n) {                                                                           \
+                    COL_S_LOAD(a, u)                                                               \
+                    COL_S_BODY(KC, a)                                                              \
+                    ++u;                                                                           \
+                }                                                                                  \
+                plim = p + 5;                                                                      \
+                if (u == ns) { K = KC; goto chunk_done; }       /* the run may go on in the next chunk */ \
+                pnext = __float_as_int(Rb[u * CRECW + 18]);                                        \
+            }                                                                                      \
+        }                                                                                          \
+        _Pragma("unroll") for (int i = 0; i < CNR; ++i) {                                          \
+            if (!(g.dbg & 1)) red_v2(cell_at(cell[i], poff), A[KC][i]);                            \
+            A[KC][i] = make_float2(0.f, 0.f);                                                                       \
+        }                                                                                          \
+        ++p; ++pw; poff += KK;                                                                     \
+        if (pw == g.K0) { pw = 0; poff = 0; }                                                      \
+        if (p > plim) {                 /* nothing left in the window */                           \
+            if (pnext == INT_MAX) goto item_done;                                                  \
+            p = pnext; pw = pnext; poff = pnext * KK; K = pnext % 6;                               \
+            continue;                                                                              \
+        }                                                                                          \
+    }
+
+        float4 aC1, aC0a, bC1, bC0a;
+        float2 aC0b, bC0b;
+        float aw, bw;
+        P2 ayv, byv;
+        for (;;) {                      // chunks
+            if (kc == nchunks) {        // all samples taken: the dummy record makes the phases drain the window
+                Rb = dummy;
+                Y = reinterpret_cast<const float2*>(dummy);
+                ns = 1;
+                u = 0;
+            } else {
+                const int s = wi.begin + kc * CCH;
+                const unsigned b = (gk + kc) & 1;
+                if (kc + 1 < nchunks) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) issue(kc + 1);
+                }
+                mbar_wait(&mbar[b], ((gk + kc) >> 1) & 1);
+                Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
+                Y = reinterpret_cast<const float2*>(ybuf + b * YS_BYTES) + (s & 1);
+                ns = min(CCH, wi.end - s);
+                u = 0;
+                ++kc;
+            }
+            if (!started) {
+                p = __float_as_int(Rb[18]);
+                K = p % 6;
+                pw = p;
+                poff = p * KK;
+                plim = p + 5;
+                started = true;
+            }
+            for (;;) {                  // phases
+                switch (K) {
+                    COL_S_PHASE(0)
+                    COL_S_PHASE(1)
+                    COL_S_PHASE(2)
+                    COL_S_PHASE(3)
+                    COL_S_PHASE(4)
+                    COL_S_PHASE(5)
+                }
+                K = 0;
+            }
+        chunk_done:;
+        }
+    item_done:
+        gk += nchunks;
+        __syncwarp();
+    }
+#undef COL_S_PHASE
+#undef COL_S_BODY
+#undef COL_S_LOAD
+#undef COL_ACC_ROW
+#undef COL_ACC
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// grid demodulation: grid[g] *= conj(prod_d m_d[g_d]); one CTA per (g0, g1) row
+// interpolation (gather) on the phase-modulated grid
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ldg_u64(const float2* p) { return __ldg(p); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+__global__ void __launch_bounds__(CWARPS * 32, 4)
+k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __restrict__ counter,
+             const float* __restrict__ rec, const float4* __restrict__ side, const float2* __restrict__ grid,
+             float2* __restrict__ y, int nb) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* ws = smem_raw + warp * IWARP_BYTES;
+    P2* pbuf = reinterpret_cast<P2*>(ws + 2 * REC_BYTES);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + PBUF_BYTES);
+    const int c = blockIdx.y;
+    const float2* gc = grid + (long long)c * g.Kprod;
+    // lanes 30, 31 shadow lane 29's cells (finite values) with the always-zero record word 30 as their column weight:
+    // their partial sums are exact zeros
+    const bool active = lane < 3 * CCOLS;
+    const int lg = active ? lane / CCOLS : 2;
+    const int lc = active ? lane - CCOLS * lg : CCOLS - 1;
+    const int lw = active ? lc : CCOLS;
+    const int KK = g.K1 * g.K2;
+    if (lane == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+    unsigned gk = 0;
+
+    for (int item = next_item(counter + c, lane); item < n_work; item = next_item(counter + c, lane)) {
+        const WorkItem wi = work[item];
+        const int q1 = wi.tile / g.nq2, q2 = wi.tile - q1 * g.nq2;
+        const float2* cell[CNR];
+        {
+            int col = q2 * CT2 + lc;
+            if (col >= g.K2) col -= g.K2;
+#pragma unroll
+            for (int i = 0; i < CNR; ++i) {
+                int row = q1 * CT1 + lg + 3 * i;
+                if (row >= g.K1) row -= g.K1;
+                cell[i] = gc + (row * g.K2 + col);
+            }
+        }
+        const int nchunks = (wi.end - wi.begin + CCH - 1) / CCH;
+        auto issue = [&](int k) {      // lane 0 only
+            const int s = wi.begin + k * CCH;
+            const int ns = min(CCH, wi.end - s);
+            const unsigned b = (gk + k) & 1;
+            mbar_expect(&mbar[b], (unsigned)(ns * CRECW * 4));
+            tma_bulk(ws + b * REC_BYTES, rec + (long long)s * CRECW, (unsigned)(ns * CRECW * 4), &mbar[b]);
+        };
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) issue(0);
+
+        P2 G[IRING][CNR];              // register ring [plane mod IRING][row]: window planes p .. p+5, the rest in flight
+#pragma unroll
+        for (int s = 0; s < IRING; ++s)
+#pragma unroll
+            for (int i = 0; i < CNR; ++i) G[s][i] = make_float2(0.f, 0.f);
+        int kc = 0, u = 0, ns = 0, s0 = 0;
+        int K = 0, p = 0, pnext = 0;
+        bool started = false;
+        const float* Rb = nullptr;
+        float4 sd = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#define COL_DOT_ROW(KC, I, C0a, C0b)                                        \
+    P2 e##I = fmul2(bc2(C0a.x), G[(KC + 0) % IRING][I]);                       \
+    ffma2_acc(e##I, bc2(C0a.y), G[(KC + 1) % IRING][I]);                        \
+    ffma2_acc(e##I, bc2(C0a.z), G[(KC + 2) % IRING][I]);                        \
+    ffma2_acc(e##I, bc2(C0a.w), G[(KC + 3) % IRING][I]);                        \
+    ffma2_acc(e##I, bc2(C0b.x), G[(KC + 4) % IRING][I]);                        \
+    ffma2_acc(e##I, bc2(C0b.y), G[(KC + 5) % IRING][I]);
+#define COL_I_LOAD(X, U)                                                                           \
+    {                                                                                              \
+        const float* R = Rb + (U) * CRECW;                                                         \
+        X##C1 = *reinterpret_cast<const float4*>(R + 4 * lg);                                      \
+        X##C0a = *reinterpret_cast<const float4*>(R + 12);                                         \
+        X##C0b = *reinterpret_cast<const float2*>(R + 16);                                         \
+        X##w = R[20 + lw];                                                                         \
+    }
+#define COL_I_BODY(KC, X, U)                                                                       \
+    {                                                                                              \
+        COL_DOT_ROW(KC, 0, X##C0a, X##C0b)                                                         \
+        COL_DOT_ROW(KC, 1, X##C0a, X##C0b)                                                         \
+        COL_DOT_ROW(KC, 2, X##C0a, X##C0b)                                                         \
+        P2 acc = fmul2(bc2(X##C1.x), e0);                                                         \
+        ffma2_acc(acc, bc2(X##C1.y), e1);                                                          \
+        ffma2_acc(acc, bc2(X##C1.z), e2);                                                          \
+        pbuf[(U) * PBUF_PITCH + lane] = fmul2(bc2(X##w), acc);                                     \
+    }
+        // phase KC: plane p sits in ring slot KC.  Take every sample whose first plane is p (counted loop over the run,
+        // as in the scatter), then replace plane p by plane p + 8 (consumed two window moves later) and, optionally,
+        // ask L2 for a plane further ahead.
+#define COL_I_PHASE(KC)                                                                            \
+    case KC: {                                                                                     \
+        if (u == ns) { K = KC; goto chunk_done; }                                                  \
+        {                                                                                          \
+            const int2 pr = *reinterpret_cast<const int2*>(Rb + u * CRECW + 18);   /* p0, run */   \
+            pnext = pr.x;                                                                          \
+            if (pnext == p) {                                                                      \
+                int n = min(pr.y, ns - u);                                                         \
+                _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                                   \
+                    COL_I_LOAD(a, u)                                                               \
+                    COL_I_LOAD(b, u + 1)                                                           \
+                    COL_I_BODY(KC, a, u)                                                           \
+                    COL_I_BODY(KC, b, u + 1)                                                       \
+                }                                                                                  \
+                if (n) {                                                                           \
+                    COL_I_LOAD(a, u)                                                               \
+                    COL_I_BODY(KC, a, u)                                                           \
+                    ++u;                                                                           \
+                }                                                                                  \
+                if (u == ns) { K = KC; goto chunk_done; }                                          \
+                pnext = __float_as_int(Rb[u * CRECW + 18]);                                        \
+            }                                                                                      \
+        }                                                                                          \
+        {                                                                                          \
+            int pl = p + IRING;                                                                    \
+            if (pl >= g.K0) pl -= g.K0;                                                            \
+            const int off = pl * KK;                                                               \
+            if (!(g.dbg & 1)) {                                                                    \
+                _Pragma("unroll") for (int i = 0; i < CNR; ++i) G[KC][i] = ldg_u64(cell_at(cell[i], off)); \
+            }                                                                                      \
+            if (g.pf_ahead) {                                                                      \
+                int pf = pl + g.pf_ahead;                                                          \
+                if (pf >= g.K0) pf -= g.K0;                                                        \
+                if (pf >= g.K0) pf = pl;    /* tiny grids */                                       \
+                const int offp = pf * KK;                                                          \
+                _Pragma("unroll") for (int i = 0; i < CNR; ++i) prefetch_l2(cell_at(cell[i], offp)); \
+            }                                                                                      \
+            ++p;                                                                                   \
+            if (pnext - p >= IRING) {   /* jump: nothing in the ring is of use, prime it again */  \
+                p = pnext - IRING;                                                                 \
+                K = pnext % IRING;                                                                 \
+                continue;                                                                          \
+            }                                                                                      \
+        }                                                                                          \
+    }
+
+        float4 aC1, aC0a, bC1, bC0a;
+        float2 aC0b, bC0b;
+        float aw, bw;
+        for (;;) {                      // chunks
+            {
+                s0 = wi.begin + kc * CCH;
+                const unsigned b = (gk + kc) & 1;
+                if (kc + 1 < nchunks) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) issue(kc + 1);
+                }
+                ns = min(CCH, wi.end - s0);
+                // phase and original index of sample `lane` of the chunk (used after the reduction)
+                if (lane < ns) sd = __ldg(side + s0 + lane);
+                mbar_wait(&mbar[b], ((gk + kc) >> 1) & 1);
+                Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
+                u = 0;
+                ++kc;
+            }
+            if (!started) {             // prime the ring: eight empty phases load planes p0 .. p0 + 7
+                const int pf = __float_as_int(Rb[18]);
+                p = pf - IRING;
+                K = pf % IRING;
+                started = true;
+            }
+            for (;;) {                  // phases
+                switch (K) {
+                    COL_I_PHASE(0)
+                    COL_I_PHASE(1)
+                    COL_I_PHASE(2)
+                    COL_I_PHASE(3)
+                    COL_I_PHASE(4)
+                    COL_I_PHASE(5)
+                    COL_I_PHASE(6)
+                    COL_I_PHASE(7)
+#if COL_IRING == 10
+                    COL_I_PHASE(8)
+                    COL_I_PHASE(9)
+#endif
+                }
+                K = 0;
+            }
+        chunk_done:
+            // ---- reduce the 32 partial sums of every sample of the chunk: lane -> (sample, half) ----
+            __syncwarp();
+            {
+                const int su = lane & 15, h = lane >> 4;
+                const P2* pb = pbuf + su * PBUF_PITCH + h * 16;
+                float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int l = 0; l < 16; ++l) {
+                    const float2 v = pb[l];
+                    sum.x += v.x;
+                    sum.y += v.y;
+                }
+                sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 16);
+                sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 16);
+                if (lane < ns) y[(long long)__float_as_int(sd.z) * nb + c] = cmul(make_float2(sd.x, sd.y), sum);
+            }
+            __syncwarp();
+            if (kc == nchunks) break;
+        }
+        gk += nchunks;
+    }
+#undef COL_I_PHASE
+#undef COL_I_BODY
+#undef COL_I_LOAD
+#undef COL_DOT_ROW
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// grid (de)modulation: grid[g] *= (conj) prod_d m_d[g_d]; one CTA per (g0, g1) row
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_demodulate(float2* __restrict__ grid, const float2* __restrict__ mod, int K0, int K1, int K2) {
     const int row = blockIdx.x;                        // g0 * K1 + g1
@@ -280,6 +561,17 @@ __global__ void k_demodulate(float2* __restrict__ grid, const float2* __restrict
     const float2* m2 = mod + K0 + K1;
     float2* dst = grid + cb + (long long)row * K2;
     for (int g2 = threadIdx.x; g2 < K2; g2 += blockDim.x) dst[g2] = cmulc(cmul(m01, __ldg(m2 + g2)), dst[g2]);
+}
+
+// out[g] = in[g] * prod_d m_d[g_d] (in == out allowed)
+__global__ void k_modulate(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ mod,
+                           int K0, int K1, int K2) {
+    const int row = blockIdx.x;
+    const int g0 = row / K1, g1 = row - g0 * K1;
+    const long long cb = (long long)blockIdx.y * K0 * K1 * K2 + (long long)row * K2;
+    const float2 m01 = cmul(__ldg(mod + g0), __ldg(mod + K0 + g1));
+    const float2* m2 = mod + K0 + K1;
+    for (int g2 = threadIdx.x; g2 < K2; g2 += blockDim.x) out[cb + g2] = cmul(cmul(m01, __ldg(m2 + g2)), in[cb + g2]);
 }
 
 }  // namespace
@@ -293,26 +585,47 @@ bool col3d_supported(const Geom& g) {
         if (g.J[d] != 6) return false;
     return g.K[0] >= 6 && g.K[1] >= CROWS && g.K[2] >= CCOLS;
 }
+// the gather's register ring runs two planes ahead of the window: planes up to K0 + 7 are wrapped with one subtraction
+bool col3d_interp_supported(const Geom& g) { return col3d_supported(g) && g.K[0] >= IRING; }
 
 static ColGeom col_geom(const Geom& g) {
     ColGeom c;
     c.K0 = g.K[0]; c.K1 = g.K[1]; c.K2 = g.K[2];
     c.nq2 = (g.K[2] + CT2 - 1) / CT2;
-    c.sg0 = ((g.N[0] - 1) & 1) ? -1.f : 1.f;
-    c.sg1 = ((g.N[1] - 1) & 1) ? -1.f : 1.f;
-    c.sg2 = ((g.N[2] - 1) & 1) ? -1.f : 1.f;
+    c.pf_ahead = 0;
+    c.dbg = 0;
+    if (const char* e = getenv("B200NUFFT_COL_DBG")) c.dbg = atoi(e);
+    if (const char* e = getenv("B200NUFFT_COL_PF")) c.pf_ahead = std::max(0, atoi(e));    // tuning knob
     c.Kprod = g.Kprod;
     return c;
 }
 
-// CTAs per coil of the persistent kernel: all SMs x 5 resident CTAs, shared between the coils of the launch
-static int col_ctas(b200nufft_plan_t p, int nb) {
+// CTAs per coil of the persistent kernels: all SMs x resident CTAs, shared between the coils of the launch
+static int col_ctas(b200nufft_plan_t p, int nb, int resident) {
     if (p->n_sm == 0) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) p->n_sm = prop.multiProcessorCount;
         if (p->n_sm <= 0) p->n_sm = 148;
     }
-    return std::max(1, (p->n_sm * 5 + nb - 1) / nb);
+    return std::max(1, (p->n_sm * resident + nb - 1) / nb);
+}
+
+static int col_attrs(b200nufft_plan_t p) {
+    if (!p->attr_col) {
+        CUDA_TRY(cudaFuncSetAttribute(k_gridding_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_interp_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * IWARP_BYTES));
+        p->attr_col = true;
+    }
+    return B200_OK;
+}
+
+static int col_counters(b200nufft_plan_t p, int nb) {
+    if (p->ccount_nb < nb) {
+        if (p->d_ccount) { CUDA_TRY(cudaFree(p->d_ccount)); p->d_ccount = nullptr; p->ccount_nb = 0; }
+        CUDA_TRY(cudaMalloc(&p->d_ccount, sizeof(int) * nb));
+        p->ccount_nb = nb;
+    }
+    return B200_OK;
 }
 
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st) {
@@ -323,39 +636,62 @@ int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st) 
     return B200_OK;
 }
 
+int col3d_modulate(b200nufft_plan_t p, const float2* in, float2* out, int nb, cudaStream_t st) {
+    const Geom& g = p->g;
+    dim3 gr((unsigned)(g.K[0] * g.K[1]), nb);
+    k_modulate<<<gr, 128, 0, st>>>(in, out, p->d_mod, g.K[0], g.K[1], g.K[2]);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// grid: phase-modulated grid
+int col3d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
+    int rc = col_attrs(p);
+    if (rc) return rc;
+    if (p->n_cwork == 0) return B200_OK;
+    rc = col_counters(p, nb);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(p->d_ccount, 0, sizeof(int) * nb, st));
+    dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, 4)), nb);
+    k_interp_col<<<gr, CWARPS * 32, CWARPS * IWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
+                                                               p->d_crec, p->d_cside, grid, y, nb);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
 // grid receives the phase-modulated adjoint (it is zeroed here, by the pre-pass)
 int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st) {
-    if (!p->attr_col) {
-        CUDA_TRY(cudaFuncSetAttribute(k_gridding_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
-        p->attr_col = true;
-    }
+    int rc = col_attrs(p);
+    if (rc) return rc;
     const long long nel = p->g.Kprod * nb;
     if (p->n_cwork == 0) {
         CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * nel, st));
         return B200_OK;
     }
-    if (p->ys_nb < nb) {
-        if (p->d_ys) { CUDA_TRY(cudaFree(p->d_ys)); p->d_ys = nullptr; p->ys_nb = 0; }
-        CUDA_TRY(cudaMalloc(&p->d_ys, sizeof(float4) * p->M * nb));
-        p->ys_nb = nb;
+    const long long Mpad = ((p->M + 1) & ~1LL) + 2;     // even coil stride (16-byte aligned TMA sources) + read slack
+    if (p->ys2_nb < nb) {
+        if (p->d_ys2) { CUDA_TRY(cudaFree(p->d_ys2)); p->d_ys2 = nullptr; p->ys2_nb = 0; }
+        CUDA_TRY(cudaMalloc(&p->d_ys2, sizeof(float2) * Mpad * nb));
+        CUDA_TRY(cudaMemsetAsync(p->d_ys2, 0, sizeof(float2) * Mpad * nb, st));
+        p->ys2_nb = nb;
     }
-    if (p->ccount_nb < nb) {
-        if (p->d_ccount) { CUDA_TRY(cudaFree(p->d_ccount)); p->d_ccount = nullptr; p->ccount_nb = 0; }
-        CUDA_TRY(cudaMalloc(&p->d_ccount, sizeof(int) * nb));
-        p->ccount_nb = nb;
-    }
+    rc = col_counters(p, nb);
+    if (rc) return rc;
     // float4 stores need a 16-byte aligned grid and an even element count; otherwise plain memset
     const bool vec = (reinterpret_cast<uintptr_t>(grid) & 15) == 0 && (nel & 1) == 0;
     if (!vec) CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * nel, st));
     {
+        // sized from the larger of the two jobs (grid zero-fill, data gather), capped: grid-stride loops inside
         const int TB = 256;
-        k_gather_sorted_col<<<(unsigned)((p->M + TB - 1) / TB), TB, 0, st>>>(
-            p->d_cside, p->M, y, p->d_ys, nb, reinterpret_cast<float4*>(grid), vec ? nel / 2 : 0, p->d_ccount);
+        const long long want = std::max<long long>((p->M + TB - 1) / TB, vec ? (nel / 2 + TB * 8 - 1) / (TB * 8) : 1);
+        const unsigned nblk = (unsigned)std::min<long long>(std::max<long long>(want, 1), 148LL * 64);
+        k_gather_sorted_col<<<nblk, TB, 0, st>>>(p->d_cside, p->M, Mpad, y, p->d_ys2, nb,
+                                                 reinterpret_cast<float4*>(grid), vec ? nel / 2 : 0, p->d_ccount);
         LAUNCH_CHECK();
     }
-    dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb)), nb);
+    dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, 5)), nb);
     k_gridding_col<<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
-                                                                 p->d_crec, p->d_ys, p->M, grid);
+                                                                 p->d_crec, p->d_ys2, Mpad, grid);
     LAUNCH_CHECK();
     return B200_OK;
 }

@@ -52,6 +52,37 @@ extern std::atomic<long long> g_launches;
         }                                                                                    \
     } while (0)
 
+// Every C entry point runs on its plan's device (or on the device that owns its first pointer argument) and RESTORES
+// the caller's current device on exit: a plan on cuda:1 must not silently switch a multi-GPU process to device 1.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        err = cudaGetDevice(&cur);
+        if (err == cudaSuccess && cur != dev) {
+            err = cudaSetDevice(dev);
+            if (err == cudaSuccess) prev = cur;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(dev)      \
+    DeviceGuard _dg(dev);   \
+    CUDA_TRY(_dg.err)
+static inline int device_of(const void* ptr) {      // device that owns a device pointer (current device if unknown)
+    cudaPointerAttributes a;
+    if (ptr && cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+    cudaGetLastError();
+    int cur = 0;
+    cudaGetDevice(&cur);
+    return cur;
+}
+
 #define LAUNCH_CHECK()                                                                       \
     do {                                                                                     \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
@@ -136,6 +167,9 @@ struct b200nufft_plan_s {
     // bin-sorted copy of the data for the tiled gridding kernel (16-byte slots)
     float4* d_ys = nullptr;
     int ys_nb = 0;
+    // sweep-ordered, phase-folded copy of the data for the column-sweep gridding kernel (8-byte slots, even coil stride)
+    float2* d_ys2 = nullptr;
+    int ys2_nb = 0;
     float2* d_ysb = nullptr;        // bin-sorted rows y[perm[i], :] for the 2-D batch kernels
     long long ysb_elems = 0;
     // scratch grids for the compositions
@@ -166,7 +200,7 @@ struct b200nufft_plan_s {
     float2* d_xc = nullptr;         // per-coil image scratch for many2one
     int xc_nb = 0;
     bool attr_b2d = false, attr_grid = false, attr_interp = false, attr_col = false;   // cudaFuncSetAttribute done on this plan's device
-    int interp_variant = 0, gridding_variant = 0, fft_variant = 0;   // 0 auto, 1 generic / cuFFT
+    int interp_variant = 0, gridding_variant = 0, fft_variant = 0;   // 0 auto, 1 generic / cuFFT, 2 tiled, 3 column sweep (interp)
     long long bytes = 0;
 };
 
@@ -187,11 +221,21 @@ bool col3d_supported(const Geom& g);
 // zeroes the grid itself (inside its pre-pass kernel)
 int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st);
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st);
+// register-resident column-sweep gather on the phase-modulated grid (needs K0 >= 8)
+bool col3d_interp_supported(const Geom& g);
+int col3d_interp(b200nufft_plan_t p, const float2* grid_mod, float2* y, int nb, cudaStream_t st);
+int col3d_modulate(b200nufft_plan_t p, const float2* in, float2* out, int nb, cudaStream_t st);
 // the gridding output is phase-modulated iff the column-sweep kernel runs (gridding variant "auto")
 static inline bool gridding_modulated(const b200nufft_plan_s* p) { return p->has_col && p->gridding_variant == 0; }
-// the tiled gather can read that modulated grid directly (k-space solvers iterate on modulated vectors)
+// interp variant 3: the column-sweep gather (reads the modulated grid).  Measured on configuration 3 it is slower than
+// the tiled gather (272 us against 254 us), so "auto" (0) keeps the tiled kernel; the variant stays selectable.
+static inline bool interp_uses_col(const b200nufft_plan_s* p) {
+    return p->has_col && p->d_mod && p->interp_variant == 3 && col3d_interp_supported(p->g);
+}
+// the gather can read that modulated grid directly (k-space solvers iterate on modulated vectors): column-sweep gather,
+// or the tiled gather's MOD instantiation
 static inline bool interp_takes_modulated(const b200nufft_plan_s* p) {
-    return p->has_col && p->d_mod && p->interp_variant != 1 && tiled_supported(p->g);
+    return p->has_col && p->d_mod && p->interp_variant != 1 && (interp_uses_col(p) || tiled_supported(p->g));
 }
 // grid_modulated: `grid` is phase-modulated (only legal when interp_takes_modulated(p))
 int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool grid_modulated);
@@ -200,7 +244,7 @@ int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cud
 // fft256.cu; `modulated`: the grid enters phase-modulated (col3d.cu)
 bool fft256_supported(const Geom& g);
 int fft256_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, int apply_sn, int x_single,
-                   const float2* sens, cudaStream_t st);
+                   const float2* sens, bool modulated, cudaStream_t st);
 int fft256_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode, float scale, bool modulated,
                    cudaStream_t st);
 int combine_coils(const float2* xc, const float2* sens, float2* s, long long N, int nb, cudaStream_t st);

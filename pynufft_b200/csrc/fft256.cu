@@ -102,9 +102,10 @@ struct PassArgs {
     int apply_sn;           // F1: multiply by sn;  I1: 1 multiply, 2 divide, 0 none
     float scale;            // I1: extra factor (1/prod(Kd))
     int sn0, sn1, sn2;      // offsets of the per-dim scaling vectors
-    const float2* mod;      // inverse passes: NULL, or the modulation table m_d[0..255] of the dimension the pass
-                            // transforms; its inputs are multiplied by conj(m_d[g]) (the column-sweep gridding
-                            // kernel, col3d.cu, leaves the grid phase-modulated)
+    const float2* mod;      // NULL, or the modulation table m_d[0..255] of the dimension the pass transforms: the
+                            // inverse passes multiply their inputs by conj(m_d[g]) (the column-sweep gridding
+                            // kernel, col3d.cu, leaves the grid phase-modulated), the forward passes multiply their
+                            // outputs by m_d[g] (the column-sweep gather reads the modulated grid)
 };
 
 // PASS: 1 = F1, 2 = F2, 3 = F3, 4 = I3, 5 = I2, 6 = I1
@@ -194,6 +195,10 @@ __global__ void __launch_bounds__(TPB) k_fft256(PassArgs a, const float2* __rest
             }
         }
     } else {
+        if (DIR < 0 && a.mod) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n) v[n] = cmul(__ldg(a.mod + t + 16 * n), v[n]);
+        }
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
             const int idx = t + 16 * n;
@@ -241,7 +246,7 @@ static int ensure_tw(b200nufft_plan_t p) {
 
 // grid <- FFT3(zero-pad(x * sn * sens))
 int fft256_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, int apply_sn, int x_single,
-                   const float2* sens, cudaStream_t st) {
+                   const float2* sens, bool modulated, cudaStream_t st) {
     int rc = ensure_tw(p);
     if (rc) return rc;
     const Geom& g = p->g;
@@ -256,12 +261,15 @@ int fft256_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, in
     a.sn0 = g.snoff[0]; a.sn1 = g.snoff[1]; a.sn2 = g.snoff[2];
     a.in = x;
     a.out = grid;
-    a.mod = nullptr;
+    const float2* mod = (modulated && p->d_mod) ? p->d_mod : nullptr;
+    a.mod = mod ? mod + 2 * FN : nullptr;
     k_fft256<1><<<dim3(g.N[0] * g.N[1] / 16, nb), TPB, 0, st>>>(a, p->d_tw256);
     LAUNCH_CHECK();
     a.in = grid;
+    a.mod = mod ? mod + FN : nullptr;
     k_fft256<2><<<dim3(g.N[0] * FN / 16, nb), TPB, 0, st>>>(a, p->d_tw256);
     LAUNCH_CHECK();
+    a.mod = mod;
     k_fft256<3><<<dim3(FN * FN / 16, nb), TPB, 0, st>>>(a, p->d_tw256);
     LAUNCH_CHECK();
     return B200_OK;

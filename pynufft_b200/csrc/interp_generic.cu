@@ -108,10 +108,19 @@ int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaS
             b200_set_error("interp: this plan / variant cannot read a phase-modulated grid");
             return B200_ERR_UNSUPPORTED;
         }
+        if (interp_uses_col(p)) return col3d_interp(p, grid, y, nb, st);
         return interp_tiled_launch(p, grid, y, nb, st, true);
     }
     if (use_bi(p, nb)) return batch2d_interp(p, grid, y, nb, st);
     if (p->interp_variant != 1 && single2d_supported(p->g)) return single2d_interp(p, grid, y, nb, st);
+    if (interp_uses_col(p)) {
+        // true grid in: one modulation pass into the plan's scratch, then the column-sweep gather
+        int rc = ensure_scratch(p, nb);
+        if (rc) return rc;
+        rc = col3d_modulate(p, grid, p->d_grid, nb, st);
+        if (rc) return rc;
+        return col3d_interp(p, p->d_grid, y, nb, st);
+    }
     if (p->interp_variant != 1 && tiled_supported(p->g)) return interp_tiled_launch(p, grid, y, nb, st, false);
     if (p->interp_variant == 2) {
         b200_set_error("interp: tiled variant requested but geometry unsupported");
@@ -148,7 +157,7 @@ int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cud
 
 extern "C" int b200nufft_interp(b200nufft_plan_t p, const b200_c64* grid, b200_c64* y, int nb, void* stream) {
     ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "interp: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream), false);
 }
 
@@ -156,7 +165,7 @@ extern "C" int b200nufft_interp(b200nufft_plan_t p, const b200_c64* grid, b200_c
 // b200nufft_kspace_modulated(plan) == 1
 extern "C" int b200nufft_interp_modulated(b200nufft_plan_t p, const b200_c64* grid, b200_c64* y, int nb, void* stream) {
     ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "interp: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return interp_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(y), nb, as_stream(stream), true);
 }
 // 1 if interp_modulated / gridding_modulated / ifft_crop_modulated all work on the phase-modulated grid
@@ -166,7 +175,7 @@ extern "C" int b200nufft_kspace_modulated(b200nufft_plan_t p) {
 
 extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {
     ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "gridding: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return gridding_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, as_stream(stream), false);
 }
 
@@ -174,6 +183,6 @@ extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c6
 // b200nufft_gridding_is_modulated(plan), the true grid otherwise)
 extern "C" int b200nufft_gridding_modulated(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {
     ARG_CHECK(p && grid && y && nb >= 1 && nb <= 65535, "gridding: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return gridding_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(grid), nb, as_stream(stream), true);
 }

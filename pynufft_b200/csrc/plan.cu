@@ -136,10 +136,13 @@ __global__ void k_build_records(Geom g, const PlanConst* __restrict__ pc,
 
 // ---- column-sweep gridding (col3d.cu): key = (column, first plane), 32-word records in sweep order ----
 // A column is a COL_T1 x COL_T2 cross-section (dims 1, 2) of first-neighbour cells; its box is 9 rows x 10 columns.
-// record words: [c1g[0..11] | c0rot[0..5] | p0 | p0 mod 6 | w10[0..9] | 0 0]
+// record words: [c1g[0..11] | c0[0..5] | p0 | run | w10[0..9] | 0 0]
 //   c1g[4 g + i] = c1t[g + 3 i] (g, i = 0..2), c1t[b] = c1[b - k1rel] (zero outside the footprint): box rows g, g+3, g+6
-//   c0rot[(p0 + j) mod 6] = c0[j]: weight of the plane slot that holds plane p0 + j
+//   c0[j]: weight of plane p0 + j (the kernels are unrolled over the window phase, so no rotation is stored)
+//   run: samples from this one to the end of its (column, first plane) bin -- the kernels' counted inner loop
 //   w10[c] = c2[c - k2rel] (zero outside the footprint): box columns
+//   every weight of a neighbour that wraps around the periodic grid (k + j >= K_d) carries the factor
+//   e^{i s_d K_d} = (-1)^(N_d - 1) of the phase-modulated grid, so that the kernels never see a sign
 // side: (P''.re, P''.im, original index, 0), P'' = prod_d exp(i (om N/2 - s dk - s (k0' - 1))): the per-offset phase
 // exp(i s (j+1)) of the reference coefficient (helper.py:148-162) is carried by the modulated grid.
 __global__ void k_col_keys(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om, long long M,
@@ -156,8 +159,8 @@ __global__ void k_col_keys(Geom g, const PlanConst* __restrict__ pc, const doubl
 }
 
 __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om,
-                              const int* __restrict__ perm, long long M, float* __restrict__ rec,
-                              float4* __restrict__ side) {
+                              const int* __restrict__ perm, long long M, int nq2, const int* __restrict__ cbin,
+                              float* __restrict__ rec, float4* __restrict__ side) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= M) return;
     const int m = perm[i];
@@ -172,10 +175,11 @@ __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const do
         dim_math(o, d, g, pc, R);
         const int k = wrap_index(R.k0 + 1, g.K[d]);
         ks[d] = k;
+        const float sgd = ((g.N[d] - 1) & 1) ? -1.f : 1.f;
         for (int j = 0; j < 6; ++j) {
-            const float cj = (float)R.c[j];
+            const float cj = (k + j >= g.K[d]) ? sgd * (float)R.c[j] : (float)R.c[j];
             if (d == 0) {
-                out[12 + (k + j) % 6] = cj;            // slot of plane k + j
+                out[12 + j] = cj;                      // plane k + j
             } else if (d == 1) {
                 const int b = k % COL_T1 + j;          // box row 0..8
                 out[4 * (b % 3) + b / 3] = cj;
@@ -186,9 +190,9 @@ __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const do
         const double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
         ph += o * (double)g.N[d] / 2.0 - s * R.dk - s * (double)(k - 1);
     }
-    const int s0 = ks[0] % 6;
+    const int key = ((ks[1] / COL_T1) * nq2 + ks[2] / COL_T2) * g.K[0] + ks[0];
     outi[18] = ks[0];
-    outi[19] = s0;
+    outi[19] = cbin[key + 1] - (int)i;
     double sn, cs;
     sincos(ph, &sn, &cs);
     side[i] = make_float4((float)cs, (float)sn, __int_as_float(m), 0.f);
@@ -279,7 +283,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     ARG_CHECK(batch >= 1, "batch must be >= 1");
     ARG_CHECK(om != nullptr || M == 0, "om is NULL");
     ARG_CHECK(alpha && alpha_len && Tmat && sn, "plan constants are NULL");
-    CUDA_TRY(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaStream_t st = as_stream(stream);
 
     b200nufft_plan_s* p = new b200nufft_plan_s();
@@ -513,7 +517,7 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         k_bin_start<<<(n_cbins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, n_cbins, d_cbin);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
-        k_col_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_cperm, M, p->d_crec, p->d_cside);
+        k_col_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_cperm, M, col_nq2, d_cbin, p->d_crec, p->d_cside);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         std::vector<int> h_cbin(n_cbins + 1, 0);
@@ -553,7 +557,7 @@ void host_pipe_destroy(b200nufft_plan_t p);   // stages.cu
 
 extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     if (!p) return B200_OK;
-    cudaSetDevice(p->device);
+    DeviceGuard dg(p->device);
     host_pipe_destroy(p);
     cudaFree(p->d_pc);
     cudaFree(p->d_om);
@@ -570,6 +574,7 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_mod);
     cudaFree(p->d_ccount);
     cudaFree(p->d_ys);
+    cudaFree(p->d_ys2);
     cudaFree(p->d_ysb);
     cudaFree(p->d_tw256);
     cudaFree(p->d_xc);
@@ -587,7 +592,7 @@ extern "C" int b200nufft_plan_get_layout(b200nufft_plan_t p) { return p ? (p->ha
 static int run_export(b200nufft_plan_t p, uint32_t* kindx, float2* udata, int* k0, void* stream) {
     ARG_CHECK(p != nullptr, "plan is NULL");
     if (p->M == 0) return B200_OK;
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int TB = 128;
     k_export<<<(unsigned)((p->M + TB - 1) / TB), TB, 0, as_stream(stream)>>>(p->g, p->d_pc, p->d_om, p->M,
                                                                             kindx, udata, k0);
@@ -635,7 +640,11 @@ extern "C" int64_t b200nufft_plan_bytes(b200nufft_plan_t p) { return p ? p->byte
 
 extern "C" int b200nufft_set_variant(b200nufft_plan_t p, int iv, int gv) {
     ARG_CHECK(p != nullptr, "plan is NULL");
-    ARG_CHECK(iv >= 0 && iv <= 2 && gv >= 0 && gv <= 2, "variant must be 0..2");
+    ARG_CHECK(iv >= 0 && iv <= 3 && gv >= 0 && gv <= 2, "interp variant must be 0..3, gridding variant 0..2");
+    if (iv == 3 && !(p->has_col && p->d_mod && col3d_interp_supported(p->g))) {
+        b200_set_error("interp variant 3 (column-sweep gather) needs a 3-D J = 6 plan with sweep records and K0 >= 10");
+        return B200_ERR_UNSUPPORTED;
+    }
     p->interp_variant = iv;
     p->gridding_variant = gv;
     p->fft_variant = (iv == 1 && gv == 1) ? 1 : 0;   // 'generic' also selects the cuFFT path

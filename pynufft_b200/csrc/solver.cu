@@ -234,12 +234,14 @@ static inline unsigned stream_blocks(long long n) {
 
 extern "C" int b200nufft_zero_scalars(double* s, int n, void* stream) {
     ARG_CHECK(s && n >= 0, "zero_scalars: bad arguments");
+    ON_DEVICE(device_of(s));
     CUDA_TRY(cudaMemsetAsync(s, 0, sizeof(double) * n, as_stream(stream)));
     return B200_OK;
 }
 
 extern "C" int b200nufft_dotc(const b200_c64* a, const b200_c64* b, int64_t n, double* out, void* stream) {
     ARG_CHECK(a && b && out && n >= 0, "dotc: bad arguments");
+    ON_DEVICE(device_of(a));
     k_dotc<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(a),
                                                                reinterpret_cast<const float2*>(b), n, out);
     LAUNCH_CHECK();
@@ -249,6 +251,7 @@ extern "C" int b200nufft_dotc(const b200_c64* a, const b200_c64* b, int64_t n, d
 extern "C" int b200nufft_cg_init(const b200_c64* b, const b200_c64* Ax, b200_c64* r, b200_c64* p, double* rsold,
                                  int64_t n, void* stream) {
     ARG_CHECK(b && Ax && r && p && rsold && n >= 0, "cg_init: bad arguments");
+    ON_DEVICE(device_of(b));
     k_cg_init<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
         reinterpret_cast<const float2*>(b), reinterpret_cast<const float2*>(Ax), reinterpret_cast<float2*>(r),
         reinterpret_cast<float2*>(p), rsold, n);
@@ -260,6 +263,7 @@ extern "C" int b200nufft_cg_update_xr(b200_c64* x, b200_c64* r, const b200_c64* 
                                       const double* rsold, const double* pAp, double* rsnew, int64_t n,
                                       void* stream) {
     ARG_CHECK(x && r && p && Ap && rsold && pAp && rsnew && n >= 0, "cg_update_xr: bad arguments");
+    ON_DEVICE(device_of(x));
     k_cg_update_xr<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
         reinterpret_cast<float2*>(x), reinterpret_cast<float2*>(r), reinterpret_cast<const float2*>(p),
         reinterpret_cast<const float2*>(Ap), rsold, pAp, rsnew, n);
@@ -270,6 +274,7 @@ extern "C" int b200nufft_cg_update_xr(b200_c64* x, b200_c64* r, const b200_c64* 
 extern "C" int b200nufft_cg_update_p(b200_c64* p, const b200_c64* r, const double* rsnew, const double* rsold,
                                      int64_t n, void* stream) {
     ARG_CHECK(p && r && rsnew && rsold && n >= 0, "cg_update_p: bad arguments");
+    ON_DEVICE(device_of(p));
     k_cg_update_p<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
         reinterpret_cast<float2*>(p), reinterpret_cast<const float2*>(r), rsnew, rsold, n);
     LAUNCH_CHECK();
@@ -278,6 +283,7 @@ extern "C" int b200nufft_cg_update_p(b200_c64* p, const b200_c64* r, const doubl
 
 extern "C" int b200nufft_cdiv(b200_c64* a, const b200_c64* b, int64_t n, void* stream) {
     ARG_CHECK(a && b && n >= 0, "cdiv: bad arguments");
+    ON_DEVICE(device_of(a));
     k_cdiv<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(a),
                                                                reinterpret_cast<const float2*>(b), n);
     LAUNCH_CHECK();
@@ -286,6 +292,7 @@ extern "C" int b200nufft_cdiv(b200_c64* a, const b200_c64* b, int64_t n, void* s
 
 extern "C" int b200nufft_cmul(b200_c64* a, const b200_c64* b, int64_t n, void* stream) {
     ARG_CHECK(a && b && n >= 0, "cmul: bad arguments");
+    ON_DEVICE(device_of(a));
     k_cmul<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(a),
                                                                reinterpret_cast<const float2*>(b), n);
     LAUNCH_CHECK();
@@ -295,7 +302,7 @@ extern "C" int b200nufft_cmul(b200_c64* a, const b200_c64* b, int64_t n, void* s
 extern "C" int b200nufft_tv_rhs(b200nufft_plan_t p, const b200_c64* AHyk, const b200_c64* d, const b200_c64* b,
                                 float mu, float lambda, b200_c64* rhs, void* stream) {
     ARG_CHECK(p && AHyk && d && b && rhs, "tv_rhs: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int TB = 256;
     k_tv_rhs<<<(unsigned)((p->g.Nprod + TB - 1) / TB), TB, 0, as_stream(stream)>>>(
         p->g, reinterpret_cast<const float2*>(AHyk), reinterpret_cast<const float2*>(d),
@@ -307,7 +314,7 @@ extern "C" int b200nufft_tv_rhs(b200nufft_plan_t p, const b200_c64* AHyk, const 
 extern "C" int b200nufft_tv_shrink(b200nufft_plan_t p, const b200_c64* x, b200_c64* d, b200_c64* b, float lambda,
                                    void* stream) {
     ARG_CHECK(p && x && d && b && lambda != 0.f, "tv_shrink: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const int TB = 256;
     k_tv_shrink<<<(unsigned)((p->g.Nprod + TB - 1) / TB), TB, 0, as_stream(stream)>>>(
         p->g, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(d), reinterpret_cast<float2*>(b), lambda);
@@ -318,6 +325,7 @@ extern "C" int b200nufft_tv_shrink(b200nufft_plan_t p, const b200_c64* x, b200_c
 extern "C" int b200nufft_tv_bregman(b200_c64* AHyk, const b200_c64* zf, const b200_c64* AHy, int64_t n,
                                     void* stream) {
     ARG_CHECK(AHyk && zf && AHy && n >= 0, "tv_bregman: bad arguments");
+    ON_DEVICE(device_of(AHyk));
     k_tv_bregman<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
         reinterpret_cast<float2*>(AHyk), reinterpret_cast<const float2*>(zf), reinterpret_cast<const float2*>(AHy), n);
     LAUNCH_CHECK();

@@ -153,7 +153,7 @@ __global__ void k_scale_inplace(float2* __restrict__ a, long long n, float f) {
 extern "C" int b200nufft_x2xx(b200nufft_plan_t p, const b200_c64* in, b200_c64* out, int nb, int div,
                               void* stream) {
     ARG_CHECK(p && in && out && nb >= 1, "x2xx: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     long long tot = p->g.Nprod * nb;
     const int TB = 256;
     k_x2xx<<<(unsigned)((tot + TB - 1) / TB), TB, 0, as_stream(stream)>>>(
@@ -165,7 +165,7 @@ extern "C" int b200nufft_x2xx(b200nufft_plan_t p, const b200_c64* in, b200_c64* 
 extern "C" int b200nufft_scale_pad(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb,
                                    int apply_sn, int x_single, const b200_c64* sens, void* stream) {
     ARG_CHECK(p && x && grid && nb >= 1 && nb <= 65535, "scale_pad: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     const Geom& g = p->g;
     const int dl = g.ndim - 1;
     const int nrows = (int)(g.Kprod / g.K[dl]);
@@ -241,7 +241,7 @@ static int fft_pruned(b200nufft_plan_t p, float2* grid, int nb, int mode, cudaSt
 //          3 forward of a zero-padded image (pruned), 4 inverse unnormalised, image corner planes only (pruned)
 extern "C" int b200nufft_fft(b200nufft_plan_t p, b200_c64* grid, int nb, int inverse, void* stream) {
     ARG_CHECK(p && grid && nb >= 1 && inverse >= 0 && inverse <= 4, "fft: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     if (inverse >= 3) {
         if (can_prune(p->g)) return fft_pruned(p, reinterpret_cast<float2*>(grid), nb, inverse, as_stream(stream));
         inverse = inverse == 3 ? 0 : 2;
@@ -278,7 +278,7 @@ static int crop_scale_impl(b200nufft_plan_t p, const float2* grid, float2* x, in
 extern "C" int b200nufft_crop_scale(b200nufft_plan_t p, const b200_c64* grid, b200_c64* x, int nb, int mode,
                                     int combine, const b200_c64* sens, void* stream) {
     ARG_CHECK(p && grid && x && nb >= 1 && mode >= 0 && mode <= 2, "crop_scale: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return crop_scale_impl(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(x), nb, mode,
                            combine, reinterpret_cast<const float2*>(sens), 1.0f, as_stream(stream));
 }
@@ -293,16 +293,33 @@ int ensure_scratch(b200nufft_plan_t p, int nb) {
 
 // pad_fft: grid = FFT(zero-pad(x * [sn] * [sens])).  Fused pruned passes when the geometry allows
 // (fft256.cu), else scale_pad + cuFFT (pruned plan for other 3-D sizes).
-extern "C" int b200nufft_pad_fft(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
-                                 int x_single, const b200_c64* sens, void* stream) {
+// `modulated`: leave the grid phase-modulated, G'[g] = G[g] prod_d m_d[g_d] (what the column-sweep gather reads)
+static int pad_fft_impl(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb, int apply_sn, int x_single,
+                        const b200_c64* sens, void* stream, bool modulated) {
     ARG_CHECK(p && x && grid && nb >= 1 && nb <= 65535, "pad_fft: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
+    if (modulated && !p->d_mod) {
+        b200_set_error("pad_fft: modulated grid requested but the plan has no modulation tables");
+        return B200_ERR_UNSUPPORTED;
+    }
     if (p->fft_variant != 1 && fft256_supported(p->g))
         return fft256_forward(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
-                              x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
+                              x_single, reinterpret_cast<const float2*>(sens), modulated, as_stream(stream));
     int rc = b200nufft_scale_pad(p, x, grid, nb, apply_sn, x_single, sens, stream);
     if (rc) return rc;
-    return b200nufft_fft(p, grid, nb, 3, stream);
+    rc = b200nufft_fft(p, grid, nb, 3, stream);
+    if (rc || !modulated) return rc;
+    return col3d_modulate(p, reinterpret_cast<const float2*>(grid), reinterpret_cast<float2*>(grid), nb, as_stream(stream));
+}
+
+extern "C" int b200nufft_pad_fft(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
+                                 int x_single, const b200_c64* sens, void* stream) {
+    return pad_fft_impl(p, x, grid, nb, apply_sn, x_single, sens, stream, false);
+}
+// the same, leaving the grid in the form b200nufft_interp_modulated reads (only when b200nufft_kspace_modulated(plan))
+extern "C" int b200nufft_pad_fft_modulated(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, int nb, int apply_sn,
+                                           int x_single, const b200_c64* sens, void* stream) {
+    return pad_fft_impl(p, x, grid, nb, apply_sn, x_single, sens, stream, true);
 }
 
 // ifft_crop: x = crop(IFFT(grid)) * f (mode 0/1/2 as crop_scale), optionally combined over coils.
@@ -312,7 +329,7 @@ extern "C" int b200nufft_pad_fft(b200nufft_plan_t p, const b200_c64* x, b200_c64
 static int ifft_crop_impl(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int nb, int mode, int combine,
                           const b200_c64* sens, void* stream, bool modulated) {
     ARG_CHECK(p && x && grid && nb >= 1 && mode >= 0 && mode <= 2, "ifft_crop: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     cudaStream_t st = as_stream(stream);
     const float scale = 1.0f / (float)p->g.Kprod;
     const bool mod = modulated && gridding_modulated(p);
@@ -356,10 +373,12 @@ static int forward_impl(b200nufft_plan_t p, const float2* x, int x_single, const
                         void* stream) {
     int rc = ensure_scratch(p, nb);
     if (rc) return rc;
-    rc = b200nufft_pad_fft(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
-                           x_single, reinterpret_cast<const b200_c64*>(sens), stream);
+    // the column-sweep gather reads the phase-modulated grid: the forward FFT passes produce it directly
+    const bool mod = interp_uses_col(p) && !use_bi(p, nb);
+    rc = pad_fft_impl(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
+                      x_single, reinterpret_cast<const b200_c64*>(sens), stream, mod);
     if (rc) return rc;
-    return interp_impl(p, p->d_grid, y, nb, as_stream(stream), false);
+    return interp_impl(p, p->d_grid, y, nb, as_stream(stream), mod);
 }
 
 static int adjoint_impl(b200nufft_plan_t p, const float2* y, float2* x, int nb, int combine, const float2* sens,
@@ -374,20 +393,20 @@ static int adjoint_impl(b200nufft_plan_t p, const float2* y, float2* x, int nb, 
 
 extern "C" int b200nufft_forward(b200nufft_plan_t p, const b200_c64* x, b200_c64* y, int nb, void* stream) {
     ARG_CHECK(p && x && y && nb >= 1, "forward: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return forward_impl(p, reinterpret_cast<const float2*>(x), 0, nullptr, reinterpret_cast<float2*>(y), nb, stream);
 }
 
 extern "C" int b200nufft_adjoint(b200nufft_plan_t p, const b200_c64* y, b200_c64* x, int nb, void* stream) {
     ARG_CHECK(p && x && y && nb >= 1, "adjoint: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return adjoint_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(x), nb, 0, nullptr, stream);
 }
 
 extern "C" int b200nufft_forward_one2many(b200nufft_plan_t p, const b200_c64* s, const b200_c64* sens,
                                           b200_c64* y, int nb, void* stream) {
     ARG_CHECK(p && s && y && nb >= 1, "forward_one2many: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return forward_impl(p, reinterpret_cast<const float2*>(s), 1, reinterpret_cast<const float2*>(sens),
                         reinterpret_cast<float2*>(y), nb, stream);
 }
@@ -395,7 +414,7 @@ extern "C" int b200nufft_forward_one2many(b200nufft_plan_t p, const b200_c64* s,
 extern "C" int b200nufft_adjoint_many2one(b200nufft_plan_t p, const b200_c64* y, const b200_c64* sens,
                                           b200_c64* s, int nb, void* stream) {
     ARG_CHECK(p && s && y && nb >= 1, "adjoint_many2one: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     return adjoint_impl(p, reinterpret_cast<const float2*>(y), reinterpret_cast<float2*>(s), nb, 1,
                         reinterpret_cast<const float2*>(sens), stream);
 }
@@ -414,7 +433,7 @@ static int ensure_io(b200nufft_plan_t p, int nb) {
 extern "C" int b200nufft_forward_host(b200nufft_plan_t p, const b200_c64* x_host, b200_c64* y_host, int nb,
                                       void* stream) {
     ARG_CHECK(p && x_host && y_host && nb >= 1, "forward_host: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     int rc = ensure_io(p, nb);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
@@ -429,7 +448,7 @@ extern "C" int b200nufft_forward_host(b200nufft_plan_t p, const b200_c64* x_host
 extern "C" int b200nufft_adjoint_host(b200nufft_plan_t p, const b200_c64* y_host, b200_c64* x_host, int nb,
                                       void* stream) {
     ARG_CHECK(p && x_host && y_host && nb >= 1, "adjoint_host: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     int rc = ensure_io(p, nb);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
@@ -501,7 +520,7 @@ static int ensure_pipe(b200nufft_plan_t p, int nb) {
 static int host_async(b200nufft_plan_t p, int op, const b200_c64* in_host, b200_c64* out_host, int nb, int slot,
                       void* stream) {
     ARG_CHECK(p && in_host && out_host && nb >= 1 && slot >= 0 && slot < B200NUFFT_HOST_SLOTS, "host_async: bad arguments");
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     int rc = ensure_pipe(p, nb);
     if (rc) return rc;
     rc = ensure_scratch(p, nb);
@@ -539,7 +558,7 @@ extern "C" int b200nufft_adjoint_host_async(b200nufft_plan_t p, const b200_c64* 
 extern "C" int b200nufft_host_wait(b200nufft_plan_t p, int op, int slot) {
     ARG_CHECK(p && (op == 0 || op == 1) && slot >= 0 && slot < B200NUFFT_HOST_SLOTS, "host_wait: bad arguments");
     if (!p->pipe.ready) return B200_OK;
-    CUDA_TRY(cudaSetDevice(p->device));
+    ON_DEVICE(p->device);
     CUDA_TRY(cudaEventSynchronize(p->pipe.ev_out[op][slot]));
     return B200_OK;
 }

@@ -484,6 +484,7 @@ class NUFFT:
         return int(self._lib.b200nufft_plan_get_layout(self._plan))
 
     def set_variant(self, interp=0, gridding=0):
-        """0 auto, 1 generic kernels, 2 tiled kernels (error if the geometry is unsupported)."""
+        """0 auto, 1 generic kernels, 2 tiled kernels (error if the geometry is unsupported); interp=3 selects the
+        column-sweep gather (csrc/col3d.cu)."""
         self._require_plan()
         _lib.check(self._lib.b200nufft_set_variant(self._plan, int(interp), int(gridding)))

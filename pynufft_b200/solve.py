@@ -131,9 +131,19 @@ def _laplacian_kernel(nufft):
 
 
 def L1TVOLS(nufft, gy, maxiter, rho):
-    """Split-Bregman total variation, device variant (solve_device.py:74-275)."""
-    if nufft.batch != 1 or gy.dim() != 1:
-        raise ValueError('L1TVOLS is single-coil (as in the reference)')
+    """Split-Bregman total variation, device variant (solve_device.py:74-275).
+
+    Multi-coil data (M, B) on a batch plan: the batched twin's closures (linalg/solve_hsa.py:275-476, AHA =
+    nufft.selfadjoint, AH = nufft.adjoint at :282-287) between the ONE Nd image the solver iterates on (:291-318)
+    and the B coils: AH = adjoint_many2one, AHA = selfadjoint_one2many2one (linalg/nufft_hsa.py:658-672, 747-769),
+    i.e. TV-SENSE with the coil maps of set_sense().  uker and the Ku = rhs solve stay single-image."""
+    multi = gy.dim() == 2
+    if multi and int(gy.shape[1]) != nufft.batch:
+        raise ValueError('y has %d coils, the plan has batch=%d' % (int(gy.shape[1]), nufft.batch))
+    if not multi and nufft.batch != 1:
+        raise ValueError('single-coil data on a batch=%d plan: pass y of shape (M, %d)' % (nufft.batch, nufft.batch))
+    AH = nufft.adjoint_many2one if multi else nufft._adjoint_device
+    AHA = nufft.selfadjoint_one2many2one if multi else nufft._selfadjoint_device
     L = nufft._lib
     st = _stream
     mu = 1.0
@@ -142,7 +152,7 @@ def L1TVOLS(nufft, gy, maxiter, rho):
     dev = nufft.device
     uker = (mu * _sampling_density(nufft).cpu().numpy() - LMBD * _laplacian_kernel(nufft)).astype(numpy.complex64)
     uker = torch.from_numpy(uker).to(dev)
-    AHy = nufft._adjoint_device(gy)
+    AHy = AH(gy)
     Nd = tuple(nufft.Nd)
     n = int(numpy.prod(Nd))
     xkp1 = torch.zeros(Nd, dtype=torch.complex64, device=dev)
@@ -157,7 +167,7 @@ def L1TVOLS(nufft, gy, maxiter, rho):
         _lib.check(L.b200nufft_pad_fft(nufft._plan, _ptr(rhs), _ptr(k), 1, 0, 0, None, st()))
         _lib.check(L.b200nufft_cdiv(_ptr(k), _ptr(uker), k.numel(), st()))
         _lib.check(L.b200nufft_ifft_crop(nufft._plan, _ptr(k), _ptr(xkp1), 1, 0, 0, None, st()))
-        zf = nufft._selfadjoint_device(xkp1)
+        zf = AHA(xkp1)
         _lib.check(L.b200nufft_tv_shrink(nufft._plan, _ptr(xkp1), _ptr(dd), _ptr(bb), LMBD, st()))
         _lib.check(L.b200nufft_tv_bregman(_ptr(AHyk), _ptr(zf), _ptr(AHy), n, st()))
     return xkp1

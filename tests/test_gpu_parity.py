@@ -226,6 +226,18 @@ def test_gridding_kernels_agree_3d(dev, geom):
         assert rel(A.y2k(y), ref_k) < TOL
         assert rel(A.adjoint(y), ref_x) < TOL
         assert rel(A.selfadjoint(x), O.adjoint(O.forward(x).astype(numpy.complex64))) < TOL
+    # column-sweep gather (interp variant 3): register ring on the phase-modulated grid, forward FFT passes emit it
+    if Kd[0] >= 10:
+        A.set_variant(3, 0)
+        assert A._kspace_modulated()
+        assert rel(A.forward(x), O.forward(x)) < TOL
+        assert rel(A.k2y(ref_k), O.k2y(ref_k)) < TOL                      # true grid in: one modulation pass first
+        km = A._y2k_device(A.to_device(y), modulated=True)
+        assert rel(A.to_host(A._k2y_device(km, modulated=True)), O.k2y(ref_k)) < TOL
+        assert rel(A.selfadjoint(x), O.adjoint(O.forward(x).astype(numpy.complex64))) < TOL
+    else:
+        with pytest.raises(Exception):
+            A.set_variant(3, 0)
     # k-space operators on phase-modulated vectors (what the CG solver iterates on): G = interp^H interp
     A.set_variant(0, 0)
     assert A._kspace_modulated() == tiled_ok

@@ -36,6 +36,20 @@ out['gridding_tiled_vs_generic'] = float(torch.linalg.norm(g_til - g_gen) / torc
 out['interp_us'] = timed(lambda: lib.b200nufft_interp(A._plan, P(k.data_ptr()), P(yv.data_ptr()), 1, st()))
 out['gridding_us'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()))
 out['memset_us'] = timed(lambda: grid.zero_())
+km = torch.empty((1,) + Kd, dtype=torch.complex64, device='cuda')
+xs = A._x2xx_device(x)
+if A._kspace_modulated():
+    lib.b200nufft_pad_fft_modulated(A._plan, P(x.data_ptr()), P(km.data_ptr()), 1, 1, 0, None, st())
+    ym = torch.empty((M,), dtype=torch.complex64, device='cuda')
+    lib.b200nufft_interp_modulated(A._plan, P(km.data_ptr()), P(ym.data_ptr()), 1, st())
+    out['interp_mod_vs_generic'] = float(torch.linalg.norm(ym - y_gen) / torch.linalg.norm(y_gen))
+    out['interp_mod_us'] = timed(lambda: lib.b200nufft_interp_modulated(A._plan, P(km.data_ptr()), P(yv.data_ptr()), 1, st()))
+    out['gridding_mod_us'] = timed(lambda: lib.b200nufft_gridding_modulated(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()))
+    out['pad_fft_mod_us'] = timed(lambda: lib.b200nufft_pad_fft_modulated(A._plan, P(x.data_ptr()), P(km.data_ptr()), 1, 1, 0, None, st()))
+    A.set_variant(2, 2)
+    out['interp_tiled_us'] = timed(lambda: lib.b200nufft_interp(A._plan, P(k.data_ptr()), P(yv.data_ptr()), 1, st()))
+    out['gridding_tiled_us'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()))
+    A.set_variant(0, 0)
 A.set_variant(1, 1)
 out['interp_generic_us'] = timed(lambda: lib.b200nufft_interp(A._plan, P(k.data_ptr()), P(yv.data_ptr()), 1, st()), it=5, warm=1)
 out['gridding_generic_us'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()), it=5, warm=1)

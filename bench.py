@@ -11,12 +11,18 @@ At N > 1 (torchrun, one rank per GPU, NCCL) every rank owns one coil of the same
 scaling: per-GPU work fixed) and the adjoint image is summed with one all-reduce per step, which is
 the only exchange the path has (adjoint_many2one).  Prints ONE JSON line on rank 0.
 
-  value      device-resident pairs/s over all ranks (CUDA events, max over ranks)
-  e2e        the same through the host API NUFFT.forward/adjoint (pinned host buffers, H2D + D2H timed)
+  value      device-resident pairs/s over all ranks: EXACTLY --steps pairs, CUDA events, max over ranks
+  sustained  the same loop repeated for >= 1 s (clocks are sampled over both regions)
+  e2e        the same through the host API (pinned host buffers, H2D + D2H of every step inside the timed region);
+             N > 1: forward_one2many / adjoint_many2one semantics -- ONE host image in (H2D on rank 0, NCCL broadcast),
+             per-coil data out and in on every rank, ONE reduced image out (D2H on rank 0)
   roofline   dominant kernel (slower of interp / gridding): algorithmic bytes (SURVEY.md 8d:
              8*K + 12*M*sum(J) + 8*M = 582.2 MB) / CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline  the oracle port of the reference's numpy/scipy CPU path on a bounded sample
---impl reference times that CPU path alone (rank 0 only).
+  config5_cg / config2  extra keys: configuration-5 CG (32 coils sharded over the N ranks) ms per iteration,
+             configuration-2 stage times (N = 1)
+--impl reference times that CPU path alone on the FULL workload (rank 0 only): every step evaluates all 2 M samples
+(interpolation and gridding in chunks of 500 k rows; plan excluded), nothing is extrapolated.
 """
 import argparse
 import json
@@ -35,6 +41,15 @@ ND, KD, JD, M = (128, 128, 128), (256, 256, 256), (6, 6, 6), 2_000_000
 WORKLOAD = '3D Nd=128^3 Kd=256^3 Jd=6^3 M=2000000 uniform-random samples, 1 coil per GPU (BASELINE.json configs[2])'
 ALGO_BYTES = 8 * 256 ** 3 + 12 * M * 18 + 8 * M          # interp or gridding, SURVEY.md 8d
 CPU_SAMPLE_M = 100_000
+CPU_CHUNK = 500_000
+
+
+def make_config(n_gpus):
+    """the SAME dict in both arms (ours / reference)"""
+    return {'workload': WORKLOAD,
+            'l2_policy': 'working set per step (134 MB grid + 192 MB + 256 MB plan records) exceeds the 126 MB L2',
+            'parallelism': ('coil-sharded x%d, one all-reduce of the adjoint image per step' % n_gpus) if n_gpus > 1
+            else 'single GPU'}
 
 
 def make_om():
@@ -50,68 +65,74 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU path (oracle port of the reference's numpy/scipy implementation), bounded sample
+# CPU path (oracle port of the reference's numpy/scipy implementation)
 # ------------------------------------------------------------------------------------------------
 class CpuPath:
-    """Full-size pad/FFT/crop (256^3) + interpolation/gridding on CPU_SAMPLE_M of the 2M samples; the
-    interp/gridding time is scaled by M / CPU_SAMPLE_M (CSR SpMV cost is linear in the rows)."""
+    """Full-size pad/FFT/crop (256^3) + CSR interpolation / gridding on the first `m` of the 2 M samples, evaluated in
+    chunks of <= 500 k rows (forward rows are independent, the adjoint is the sum of the per-chunk spH . y;
+    BASELINE.md section 3).  m = M: the whole workload, nothing scaled.  m < M (the bounded cpu_baseline leg of the GPU
+    arm): the interpolation / gridding time is scaled by M / m (CSR SpMV cost is linear in the rows)."""
 
-    def __init__(self):
+    def __init__(self, m):
         from oracle import nufft_oracle as orc
-        om = make_om()[:CPU_SAMPLE_M]
-        self.O = orc.NUFFT()
-        self.O.plan(om, ND, KD, JD)
+        om = make_om()[:m]
+        self.m = m
+        self.parts = []
+        for s in range(0, m, CPU_CHUNK):
+            O = orc.NUFFT()
+            O.plan(om[s:s + CPU_CHUNK], ND, KD, JD)
+            self.parts.append(O)
         rng = numpy.random.default_rng(1)
         self.x = (rng.standard_normal(ND) + 1j * rng.standard_normal(ND)).astype(numpy.complex64)
-        self.scale = M / CPU_SAMPLE_M
+        self.scale = M / m
 
     def pair_seconds(self):
-        O = self.O
+        O0 = self.parts[0]
         t = time.perf_counter
-        t0 = t(); k = O.xx2k(O.x2xx(self.x)); t1 = t()
-        y = O.k2y(k); t2 = t()
-        k2 = O.y2k(y.astype(numpy.complex64)); t3 = t()
-        O.xx2x(O.k2xx(k2)); t4 = t()
+        t0 = t()
+        k = O0.xx2k(O0.x2xx(self.x))
+        t1 = t()
+        ys = [O.k2y(k) for O in self.parts]
+        t2 = t()
+        k2 = None
+        for O, y in zip(self.parts, ys):
+            kk = O.y2k(y.astype(numpy.complex64))
+            k2 = kk if k2 is None else k2 + kk
+        t3 = t()
+        O0.xx2x(O0.k2xx(k2))
+        t4 = t()
         return (t1 - t0) + (t4 - t3) + self.scale * ((t2 - t1) + (t3 - t2))
 
-    @staticmethod
-    def describe():
+    def describe(self):
+        if self.m == M:
+            return ('oracle port of the reference numpy/scipy CPU path, FULL workload: scale+pad+fftn(256^3)+ifftn+crop and '
+                    'CSR interpolation+gridding of all %d samples in %d chunks of <= %d rows (plan excluded); '
+                    'single-threaded like the reference (numpy.fft + scipy CSR SpMV)' % (M, len(self.parts), CPU_CHUNK))
         return ('oracle port of the reference numpy/scipy CPU path: full-size scale+pad+fftn(256^3)+ifftn+crop, '
                 'CSR interpolation+gridding on %d of %d samples scaled x%d; single-threaded like the reference '
-                '(numpy.fft + scipy CSR SpMV)' % (CPU_SAMPLE_M, M, M // CPU_SAMPLE_M))
-
-
-REFERENCE_BUDGET_S = 150.0      # wall-clock cap of the --impl reference run (the CPU path needs ~2.5 s per sampled step)
+                '(numpy.fft + scipy CSR SpMV)' % (self.m, M, M // self.m))
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    t_start = time.perf_counter()
-    cpu = CpuPath()
-    ts = []
-    done_warm = 0
+    t_plan = time.perf_counter()
+    cpu = CpuPath(M)
+    t_plan = time.perf_counter() - t_plan
     for _ in range(max(args.warmup, 0)):
-        if done_warm >= 1 and time.perf_counter() - t_start > 0.25 * REFERENCE_BUDGET_S:
-            break
         cpu.pair_seconds()
-        done_warm += 1
-    for _ in range(args.steps):
-        ts.append(cpu.pair_seconds())
-        if len(ts) >= 3 and time.perf_counter() - t_start > REFERENCE_BUDGET_S:
-            break                      # bounded: the remaining steps would repeat the same deterministic CPU work
+    ts = [cpu.pair_seconds() for _ in range(args.steps)]
     sec = float(numpy.mean(ts))
     v = 1.0 / sec
-    sample = CpuPath.describe() + '; %d of %d steps (and %d of %d warm-up steps) executed inside the %.0f s budget' % (
-        len(ts), args.steps, done_warm, args.warmup, REFERENCE_BUDGET_S)
     line = {
         'impl': 'reference', 'metric': 'NUFFT forward+adjoint pairs/s', 'value': v, 'unit': 'pairs/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD},
+        'config': make_config(args.gpus),
         'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': 1, 'cores_available': os.cpu_count(),
-                         'kind': 'port', 'sample': sample},
+                         'kind': 'port', 'sample': cpu.describe()},
         'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'plan_seconds': t_plan, 'measured': 'every step evaluated in full; nothing extrapolated',
     }
     print(json.dumps(line), flush=True)
 
@@ -245,16 +266,20 @@ def run_ours(args, rank, world, local_rank):
     l0 = lib.b200nufft_launch_count()
     tw0 = time.perf_counter()
     ms = timed(step, args.steps, 0, drain)
-    tw1 = time.perf_counter()
     launches = lib.b200nufft_launch_count() - l0
-    clk = clocks.stop(tw0, tw1)
     value = world * args.steps / (ms * 1e-3)
+    # the same loop sustained for >= 1 s (the K-step region above is only K * 0.7 ms long)
+    sus_iters = max(args.steps, int(1.2 / max(ms / args.steps * 1e-3, 1e-6)))
+    ms_sus = timed(step, sus_iters, 0, drain)
+    tw1 = time.perf_counter()
+    clk = clocks.stop(tw0, tw1)
+    sustained = {'value': world * sus_iters / (ms_sus * 1e-3), 'unit': 'pairs/s', 'steps': sus_iters,
+                 'seconds': ms_sus * 1e-3, 'ms_per_step': ms_sus / sus_iters}
 
     # ---- e2e: host API, pinned host buffers, H2D + D2H of every step inside the timed region ----
-    # A step = forward of a host image + adjoint of a host data vector, each delivered back to the host.  The host API
-    # is used in its pipelined form (NUFFT.forward/adjoint(..., slot=s) + wait): NS steps are in flight, so the copy-in,
-    # the kernels and the copy-out of neighbouring steps overlap; every step still moves all of its inputs and outputs
-    # over PCIe.
+    # A step = forward of a host image + adjoint of a host data vector, each delivered back to the host.  NS steps are in
+    # flight, so the copy-in, the kernels and the copy-out of neighbouring steps overlap; every step still moves all of
+    # its inputs and outputs over PCIe.
     def pinned(shape):
         return torch.empty(shape, dtype=torch.complex64).pin_memory()
     NS = 3                                                       # steps in flight (staging slots used)
@@ -266,63 +291,87 @@ def run_ours(args, rank, world, local_rank):
     for s_ in range(1, NS):
         x_hosts[s_].copy_(x_host)
         y_in[s_].copy_(y_in[0])
-    # coil-sharded many2one through the host boundary (N > 1): H2D y on a copy-in stream, adjoint, ONE asynchronous
-    # all-reduce on the device, D2H on a copy-out stream; the same two-slot pipeline as the single-GPU host API
-    y_devs = [torch.empty((M,), dtype=torch.complex64, device=dev) for _ in range(NS)]
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    ev_in = [torch.cuda.Event() for _ in range(NS)]
-    ev_comp = [torch.cuda.Event() for _ in range(NS)]
-    ev_out = [torch.cuda.Event() for _ in range(NS)]
-    keep = [None] * NS
 
-    def dist_adjoint(s):
-        cur = torch.cuda.current_stream()
-        s_in.wait_event(ev_comp[s])                      # the adjoint that last read y_devs[s] is done
-        with torch.cuda.stream(s_in):
-            y_devs[s].copy_(y_in[s], non_blocking=True)
-            ev_in[s].record()
-        cur.wait_event(ev_in[s])
-        xa = A._adjoint_device(y_devs[s])
-        ev_comp[s].record()
-        work = dist.all_reduce(xa, async_op=True)
-        with torch.cuda.stream(s_out):
-            work.wait()                                  # the copy-out stream (not the compute stream) waits for NCCL
-            xa_out[s].copy_(xa, non_blocking=True)
-            ev_out[s].record()
-        xa.record_stream(s_out)
-        keep[s] = xa
-
-    def e2e_run(iters):
-        for i in range(iters):
-            s = i % NS
-            if i >= NS:
-                A.wait('forward', s)
-                if dist is None:
+    if dist is None:
+        def e2e_run(iters):
+            for i in range(iters):
+                s = i % NS
+                if i >= NS:
+                    A.wait('forward', s)
                     A.wait('adjoint', s)
-                else:
-                    ev_out[s].synchronize()
-            A.forward(x_hosts[s].numpy(), out=y_out[s].numpy(), slot=s)
-            if dist is None:
+                A.forward(x_hosts[s].numpy(), out=y_out[s].numpy(), slot=s)
                 A.adjoint(y_in[s].numpy(), out=xa_out[s].numpy(), slot=s)
-            else:
-                dist_adjoint(s)
-        for s in range(NS):
-            A.wait('forward', s)
-            if dist is None:
+            for s in range(NS):
+                A.wait('forward', s)
                 A.wait('adjoint', s)
-            else:
+        h2d = x_host.numel() * 8 + y_in[0].numel() * 8
+        d2h = y_out[0].numel() * 8 + xa_out[0].numel() * 8
+        e2e_mode = 'pipelined host API (NUFFT.forward / adjoint(..., slot) + wait), %d steps in flight' % NS
+    else:
+        # coil-sharded one2many / many2one through the host boundary: the ONE image enters on rank 0 and is broadcast
+        # over NVLink; every rank returns its coil's data (D2H) and takes its coil's data (H2D); the all-reduced image
+        # leaves from rank 0 only.  Per-rank PCIe traffic: rank 0 65.6 MB, the others 32 MB (the per-coil data).
+        x_devs = [torch.empty(ND, dtype=torch.complex64, device=dev) for _ in range(NS)]
+        y_devs = [torch.empty((M,), dtype=torch.complex64, device=dev) for _ in range(NS)]
+        ev_in = [torch.cuda.Event() for _ in range(NS)]
+        ev_yin = [torch.cuda.Event() for _ in range(NS)]
+        ev_comp = [torch.cuda.Event() for _ in range(NS)]
+        ev_fwd = [torch.cuda.Event() for _ in range(NS)]
+        ev_out = [torch.cuda.Event() for _ in range(NS)]
+        keep = [None] * NS
+
+        def dist_step(s):
+            cur = torch.cuda.current_stream()
+            s_in.wait_event(ev_comp[s])                      # the operators that last read slot s are done
+            with torch.cuda.stream(s_in):
+                if rank == 0:
+                    x_devs[s].copy_(x_hosts[s], non_blocking=True)
+                ev_in[s].record()
+                y_devs[s].copy_(y_in[s], non_blocking=True)
+                ev_yin[s].record()
+            cur.wait_event(ev_in[s])
+            dist.broadcast(x_devs[s], src=0)                 # NCCL over NVLink instead of N host copies of the image
+            y = A._forward_device(x_devs[s])
+            ev_fwd[s].record()
+            cur.wait_event(ev_yin[s])
+            xa = A._adjoint_device(y_devs[s])
+            ev_comp[s].record()
+            work = dist.all_reduce(xa, async_op=True)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_fwd[s])
+                y_out[s].copy_(y, non_blocking=True)
+                work.wait()                                  # the copy-out stream (not the compute stream) waits for NCCL
+                if rank == 0:
+                    xa_out[s].copy_(xa, non_blocking=True)
+                ev_out[s].record()
+            y.record_stream(s_out)
+            xa.record_stream(s_out)
+            keep[s] = (y, xa)
+
+        def e2e_run(iters):
+            for i in range(iters):
+                s = i % NS
+                if i >= NS:
+                    ev_out[s].synchronize()
+                dist_step(s)
+            for s in range(NS):
                 ev_out[s].synchronize()
+        # bytes per step summed over the ranks
+        h2d = x_host.numel() * 8 + world * y_in[0].numel() * 8
+        d2h = world * y_out[0].numel() * 8 + xa_out[0].numel() * 8
+        e2e_mode = ('coil-sharded forward_one2many + adjoint_many2one through the host boundary, %d steps in flight: image '
+                    'H2D on rank 0 + NCCL broadcast, per-coil data D2H / H2D on every rank, all-reduce, image D2H on '
+                    'rank 0; bytes are summed over the ranks' % NS)
     e2e_iters = max(2 * NS, min(args.steps, 60))
     e2e_run(2 * NS)
     ms_e2e = timed(lambda: e2e_run(e2e_iters), 1, 0)
     e2e_value = world * e2e_iters / (ms_e2e * 1e-3)
-    h2d = x_host.numel() * 8 + y_in[0].numel() * 8
-    d2h = y_out[0].numel() * 8 + xa_out[0].numel() * 8
+
     # the blocking host calls (one step at a time, no overlap), for comparison
     def e2e_blocking():
         A.forward(x_hosts[0].numpy(), out=y_out[0].numpy())
-        if dist is None:
-            A.adjoint(y_in[0].numpy(), out=xa_out[0].numpy())
+        A.adjoint(y_in[0].numpy(), out=xa_out[0].numpy())
     blk_iters = 10
     ms_blk = timed(e2e_blocking, blk_iters, 2) if dist is None else None
 
@@ -340,8 +389,8 @@ def run_ours(args, rank, world, local_rank):
     kern['pad_fft'] = timed(lambda: lib.b200nufft_pad_fft(A._plan, P(x.data_ptr()), P(grid.data_ptr()), 1, 1, 0, None, st()), kit, 3) / kit
     kern['interp'] = timed(lambda: lib.b200nufft_interp(A._plan, P(grid.data_ptr()), P(yv.data_ptr()), 1, st()), kit, 3) / kit
     # the adjoint's own pair of stages: the column-sweep gridding leaves the grid phase-modulated and the fused inverse
-    # passes undo it (csrc/col3d.cu); "gridding" = the whole stage: grid zero-fill (on a side stream) beside the
-    # sorted-data pre-gather, then the scatter kernel
+    # passes undo it (csrc/col3d.cu); "gridding" = the whole stage as `adjoint` runs it: pre-pass (grid zero-fill, sorted
+    # data gather) + scatter kernel.  gridding_true_grid = b200nufft_gridding, the y2k stage of the API (one more pass)
     kern['gridding'] = timed(lambda: lib.b200nufft_gridding_modulated(A._plan, P(yv.data_ptr()), P(grid.data_ptr()), 1, st()), kit, 3) / kit
     kern['memset_grid'] = timed(lambda: grid.zero_(), kit, 3) / kit
     kern['ifft_crop'] = timed(lambda: lib.b200nufft_ifft_crop_modulated(A._plan, P(grid.data_ptr()), P(xo.data_ptr()), 1, 1, 0, None, st()), kit, 3) / kit
@@ -358,31 +407,98 @@ def run_ours(args, rank, world, local_rank):
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes': ALGO_BYTES,
                 'interp_GBps': ALGO_BYTES / (kern['interp'] * 1e-3) / 1e9,
-                'gridding_GBps': ALGO_BYTES / (kern['gridding'] * 1e-3) / 1e9}
+                'gridding_GBps': ALGO_BYTES / (kern['gridding'] * 1e-3) / 1e9,
+                'gridding_true_grid_GBps': ALGO_BYTES / (kern['gridding_true_grid'] * 1e-3) / 1e9}
+    del grid, yv, xo
+
+    # ---- extra: configuration 5 (BASELINE configs[4]): 3-D 128^3, 32 coils sharded by coil over the N ranks, k-space CG
+    # with the dot products all-reduced; ms per iteration from the difference of two runs (setup excluded) ----
+    config5 = None
+    plan_bytes = int(lib.b200nufft_plan_bytes(A._plan))
+    if not args.no_extras:
+        from pynufft_b200.dist import CoilShardedNUFFT, shard_coils
+        A.release()
+        total_coils = 32
+        sl = shard_coils(total_coils, world, rank)
+        nloc = sl.stop - sl.start
+        A5 = pynufft_b200.NUFFT(dev)
+        A5.plan(om, ND, KD, JD, batch=nloc)
+        # one rank: the same solver without collectives (CoilShardedNUFFT needs a process group)
+        solve5 = (lambda it: A5._solve_device(y5, 'cg', maxiter=it)) if dist is None else \
+            (lambda it, op=CoilShardedNUFFT(A5, total_coils): op.solve_cg(y5, maxiter=it))
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        y5 = torch.view_as_complex(torch.randn((M, nloc, 2), generator=g, device=dev))
+
+        def cg_ms(iters):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            solve5(iters)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        cg_ms(1)                                                 # warm-up (allocations, cuFFT / attribute set-up)
+        lo, hi = 2, 8
+        t_lo, t_hi = cg_ms(lo), cg_ms(hi)
+        config5 = {'coils_total': total_coils, 'coils_per_gpu': nloc, 'ms_per_iter': (t_hi - t_lo) / (hi - lo),
+                   'iters_timed': hi - lo, 'note': 'k-space CG (solve_device.py:351-481), dot products all-reduced over the '
+                   'coil shards; device-resident, CUDA events, max over ranks'}
+        del y5, solve5
+        A5.release()
+
+    # ---- extra: configuration 2 (2-D 256^2 / 512^2 / 6^2, 32 coils, golden-angle radial 402 x 512) stage times ----
+    config2 = None
+    if not args.no_extras and world == 1:
+        th = numpy.arange(402) * numpy.pi * (numpy.sqrt(5.0) - 1.0) / 2.0
+        r = numpy.pi * (numpy.arange(512) - 256) / 256
+        om2 = numpy.stack([numpy.outer(numpy.cos(th), r), numpy.outer(numpy.sin(th), r)], -1).reshape(-1, 2)
+        A2 = pynufft_b200.NUFFT(dev)
+        A2.plan(om2, (256, 256), (512, 512), (6, 6), batch=32)
+        s2 = torch.view_as_complex(torch.randn((256, 256, 2), device=dev))
+        y2 = A2.forward_one2many(s2)
+        k2 = A2._y2k_device(y2)
+        k2s = A2._grid_storage(k2)[0]
+        M2 = om2.shape[0]
+        algo2 = 8 * 32 * 512 * 512 + 12 * M2 * 12 + 8 * 32 * M2
+        c2t = {}
+        c2t['interp'] = timed(lambda: lib.b200nufft_interp(A2._plan, P(k2s.data_ptr()), P(y2.data_ptr()), 32, st()), 30, 3) / 30
+        c2t['gridding'] = timed(lambda: lib.b200nufft_gridding(A2._plan, P(y2.data_ptr()), P(k2s.data_ptr()), 32, st()), 30, 3) / 30
+        c2t['forward_one2many'] = timed(lambda: A2.forward_one2many(s2), 30, 3) / 30
+        c2t['adjoint_many2one'] = timed(lambda: A2.adjoint_many2one(y2), 30, 3) / 30
+        config2 = {'ms': c2t, 'algorithmic_bytes': algo2,
+                   'interp_frac_of_peak': algo2 / (c2t['interp'] * 1e-3) / 1e9 / peak,
+                   'gridding_frac_of_peak': algo2 / (c2t['gridding'] * 1e-3) / 1e9 / peak}
+        A2.release()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = CpuPath()
+        cpu = CpuPath(CPU_SAMPLE_M)
         cpu.pair_seconds()
         secs = [cpu.pair_seconds() for _ in range(3)]
         cpu_baseline = {'value': 1.0 / float(numpy.mean(secs)), 'unit': 'pairs/s', 'cores': 1,
-                        'cores_available': os.cpu_count(), 'kind': 'port', 'sample': CpuPath.describe()}
+                        'cores_available': os.cpu_count(), 'kind': 'port', 'sample': cpu.describe()}
 
     if rank == 0:
         line = {
             'metric': 'NUFFT forward+adjoint pairs/s', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'l2_policy': 'working set per step (134 MB grid + 192 MB + 288 MB plan records) exceeds the 126 MB L2',
-                       'parallelism': 'coil-sharded x%d, one all-reduce of the adjoint image per step' % world if world > 1 else 'single GPU',
-                       'plan_seconds': plan_s, 'plan_bytes': int(lib.b200nufft_plan_bytes(A._plan))},
+            'config': make_config(world),
             'clocks': clk,
             'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': ms_e2e / e2e_iters, 'mode': 'pipelined host API, %d steps in flight' % NS,
-                    'blocking_ms_per_step': (ms_blk / blk_iters) if ms_blk else None},
+                    'ms_per_step': ms_e2e / e2e_iters, 'mode': e2e_mode,
+                    'blocking_ms_per_step': (ms_blk / blk_iters) if ms_blk else None,
+                    'blocking_value': (blk_iters / (ms_blk * 1e-3)) if ms_blk else None},
             'gpu_launches': int(launches),
             'roofline': roofline,
             'kernel_ms': kern,
+            'sustained': sustained,
+            'config5_cg': config5,
+            'config2': config2,
+            'plan_seconds': plan_s, 'plan_bytes': plan_bytes,
             'cpu_baseline': cpu_baseline,
         }
         print(json.dumps(line), flush=True)
@@ -398,17 +514,22 @@ def ctypes_ptr(v):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=None, help='default: 200 (GPU arm), 10 (reference arm: ~6 s of CPU each)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extras', action='store_true', help='skip the configuration-5 / configuration-2 extra keys')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
+        if args.steps is None:
+            args.steps = 10
         run_reference(args, rank)
         return
+    if args.steps is None:
+        args.steps = 200
     args.warmup = max(args.warmup, 3)
     run_ours(args, rank, world, local_rank)
 

@@ -124,6 +124,13 @@ int b200nufft_pad_fft(b200nufft_plan_t plan, const b200_c64* x, b200_c64* grid, 
 int b200nufft_ifft_crop(b200nufft_plan_t plan, b200_c64* grid, b200_c64* x, int nb, int mode,
                         int combine, const b200_c64* sens, void* stream);
 
+/* Concurrency contract: a plan owns its scratch grids, sorted-data buffers, work counters, staging buffers and cuFFT
+ * handles (the stream of a handle is rebound per call).  ONE plan is therefore single-stream and single-thread: calls on
+ * the same plan must be issued from one host thread and ordered on one CUDA stream (the pipelined host entry points
+ * manage their own copy streams and events).  Use one plan per stream / thread for concurrent work.  Every entry point
+ * runs on the plan's device (or on the device that owns its first pointer argument) and restores the caller's current
+ * device before it returns.                                                                                          */
+
 /* ---- compositions (plan-owned scratch grids) -------------------------------------------------
  * forward  : _forward_device  (:555-572)  x image(nb) -> y (M, nb)
  * adjoint  : _adjoint_device  (:617-633)  y (M, nb)   -> x image(nb)        (= A^H y / prod(Kd))

@@ -11,6 +11,8 @@ LIB = os.path.join(HERE, 'libb200nufft.so')
 SOURCES = ['plan.cu', 'stages.cu', 'interp_generic.cu', 'col3d.cu', 'interp_tiled.cu', 'grid_tiled.cu', 'fft256.cu', 'batch2d.cu', 'single2d.cu', 'solver.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
+# tuning experiments: extra -D definitions (part of the source hash, so a change rebuilds the library)
+NVCC_FLAGS += os.environ.get('B200NUFFT_NVCC_DEFS', '').split()
 
 
 def _nvcc():
@@ -18,6 +20,37 @@ def _nvcc():
     if not os.path.exists(exe):
         raise RuntimeError('nvcc not found; libb200nufft.so cannot be built')
     return exe
+
+
+HASHFILE = LIB + '.srchash'
+
+
+def source_hash():
+    """sha256 over the CUDA sources, the internal headers and the C header: what the shared library was built from.
+    build() stores it beside the library; _lib.load() compares, so a stale binary is rebuilt instead of being loaded
+    silently (the .so is git-ignored, so it can outlive a source change)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h')))
+    files.append(os.path.join(HERE, '..', 'include', 'b200nufft.h'))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def built_hash():
+    try:
+        with open(HASHFILE) as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
+def is_current():
+    return os.path.exists(LIB) and built_hash() == source_hash()
 
 
 def _stale(target, deps):
@@ -34,6 +67,15 @@ def build(force=False, verbose=False):
     headers.append(os.path.join(HERE, '..', 'include', 'b200nufft.h'))
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
+    # a library built from other sources / flags than the ones in the tree: the objects are of unknown origin too, unless
+    # their own hash record says otherwise
+    objhash = os.path.join(objdir, 'srchash')
+    try:
+        objs_current = open(objhash).read().strip() == source_hash()
+    except OSError:
+        objs_current = False
+    if not objs_current and not is_current():
+        force = True
     jobs = []
     objs = []
     for s in srcs:
@@ -54,9 +96,13 @@ def build(force=False, verbose=False):
     if verbose:
         for l in logs:
             sys.stderr.write(l)
-    if jobs or force or _stale(LIB, objs):
+    if jobs or force or _stale(LIB, objs) or not is_current():
         cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcufft', '-Xlinker', '-rpath', '-Xlinker', '/usr/local/cuda/lib64']
         run(cmd)
+        with open(HASHFILE, 'w') as fh:
+            fh.write(source_hash() + '\n')
+        with open(objhash, 'w') as fh:
+            fh.write(source_hash() + '\n')
     return LIB
 
 

@@ -71,14 +71,15 @@ class B200NufftError(RuntimeError):
 
 
 def load(build_if_missing=True):
-    """Load (building first if needed) the C-ABI library; raises if that is impossible."""
+    """Load the C-ABI library, (re)building it first when it is missing or stale (the source hash stored beside the
+    library differs from the sources in the tree); raises if that is impossible."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIBPATH):
+    from . import _build
+    if not _build.is_current():          # missing, or built from other sources than the ones in the tree (source hash)
         if not build_if_missing:
-            raise B200NufftError('libb200nufft.so is missing: run `python -m pynufft_b200._build`')
-        from . import _build
+            raise B200NufftError('libb200nufft.so is missing or stale: run `python -m pynufft_b200._build`')
         _build.build()
     lib = ctypes.CDLL(LIBPATH)
     for name, (res, args) in SIGNATURES.items():

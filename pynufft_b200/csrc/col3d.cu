@@ -140,7 +140,13 @@ __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M
 // ---------------------------------------------------------------------------------------------------------
 // gridding (scatter): produces the phase-modulated grid
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CWARPS * 32, 4)
+#ifndef COL_S_PAIR
+#define COL_S_PAIR 1
+#endif
+#ifndef COL_S_CTAS
+#define COL_S_CTAS 4
+#endif
+__global__ void __launch_bounds__(CWARPS * 32, COL_S_CTAS)
 k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __restrict__ counter,
                const float* __restrict__ rec, const float2* __restrict__ ys, long long Mpad, float2* __restrict__ grid) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -239,6 +245,26 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         COL_ACC_ROW(KC, 1, t1, X##C0a, X##C0b)                                                     \
         COL_ACC_ROW(KC, 2, t2, X##C0a, X##C0b)                                                     \
     }
+#if COL_S_PAIR
+#define COL_S_RUN(KC)                                                                              \
+    _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                           \
+        COL_S_LOAD(a, u)                                                                           \
+        COL_S_LOAD(b, u + 1)                                                                       \
+        COL_S_BODY(KC, a)                                                                          \
+        COL_S_BODY(KC, b)                                                                          \
+    }                                                                                              \
+    if (n) {                                                                                       \
+        COL_S_LOAD(a, u)                                                                           \
+        COL_S_BODY(KC, a)                                                                          \
+        ++u;                                                                                       \
+    }
+#else
+#define COL_S_RUN(KC)                                                                              \
+    _Pragma("unroll 1") for (; n > 0; --n, ++u) {                                                  \
+        COL_S_LOAD(a, u)                                                                           \
+        COL_S_BODY(KC, a)                                                                          \
+    }
+#endif
         // phase KC: plane p sits in slot KC.  Take every sample whose first plane is p -- the record carries the length of
         // the run of samples that share its (column, first plane), so this is a counted loop (two samples per trip, all
         // loads ahead of the math) instead of a load -> compare -> branch chain per sample -- then retire plane p.
@@ -330,6 +356,7 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         __syncwarp();
     }
 #undef COL_S_PHASE
+#undef COL_S_RUN
 #undef COL_S_BODY
 #undef COL_S_LOAD
 #undef COL_ACC_ROW
@@ -689,7 +716,7 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
                                                  reinterpret_cast<float4*>(grid), vec ? nel / 2 : 0, p->d_ccount);
         LAUNCH_CHECK();
     }
-    dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, 5)), nb);
+    dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, COL_S_CTAS)), nb);
     k_gridding_col<<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
                                                                  p->d_crec, p->d_ys2, Mpad, grid);
     LAUNCH_CHECK();

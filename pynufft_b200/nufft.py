@@ -14,6 +14,11 @@ Method names, argument meaning, return values and error behaviour follow the ref
   set_sense, reset_sense, s2x, x2s, forward_one2many, adjoint_many2one, selfadjoint_one2many2one
 
 There is no CPU processor: `NUFFT()` without a CUDA device raises.
+
+Concurrency contract (as the reference, whose kernels are queued on one reikna Thread): a plan owns its scratch grids,
+staging buffers and cuFFT handles, so ONE plan is single-stream and single-thread -- issue its calls from one thread on
+one CUDA stream at a time (the pipelined host API manages its own copy streams).  Use one NUFFT object per stream /
+thread for concurrent work.  Every library call runs on the plan's device and restores the caller's current device.
 """
 import ctypes
 
@@ -29,8 +34,9 @@ def _ptr(t):
     return _vp(t.data_ptr())
 
 
-def _stream():
-    return _vp(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """cudaStream_t of torch's current stream ON `device` (the plan's device, which need not be the current one)"""
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _as_device(device_indx):
@@ -71,6 +77,9 @@ class NUFFT:
         self.ndims = 0
         self.ft_axes = ()
         self.batch = None
+
+    def _stream(self):
+        return _stream(self.device)
 
     def __del__(self):
         try:
@@ -130,7 +139,7 @@ class NUFFT:
             rc = self._lib.b200nufft_plan_create(
                 ctypes.byref(handle), self.device.index, nd, Nd_a.ctypes.data, Kd_a.ctypes.data, Jd_a.ctypes.data,
                 M, om.ctypes.data, 1 if batch is None else int(batch), alpha.ctypes.data, alpha_len.ctypes.data,
-                Tm.ctypes.data, tensor_sn.ctypes.data, _stream())
+                Tm.ctypes.data, tensor_sn.ctypes.data, self._stream())
         _lib.check(rc)
         self._plan = handle
 
@@ -217,7 +226,7 @@ class NUFFT:
         x = self._check_dev(x, self.Nd, 'x')
         out = torch.empty_like(x)
         _lib.check(self._lib.b200nufft_x2xx(self._plan, _ptr(x), _ptr(out), self._nb_of(x, self.ndims, 'x'), 0,
-                                            _stream()))
+                                            self._stream()))
         return out
 
     def _xx2x_device(self, xx):
@@ -228,7 +237,7 @@ class NUFFT:
         xx = self._check_dev(xx, self.Nd, 'xx')
         nb = self._nb_of(xx, self.ndims, 'xx')
         view, store = self._new_grid(nb, xx.dim() == self.ndims + 1)
-        _lib.check(self._lib.b200nufft_pad_fft(self._plan, _ptr(xx), _ptr(store), nb, 0, 0, None, _stream()))
+        _lib.check(self._lib.b200nufft_pad_fft(self._plan, _ptr(xx), _ptr(store), nb, 0, 0, None, self._stream()))
         return view
 
     def _k2y_device(self, k, modulated=False):
@@ -237,7 +246,7 @@ class NUFFT:
         store, nb, batched = self._grid_storage(k)
         y = torch.empty((self.M, nb) if batched else (self.M,), dtype=torch.complex64, device=self.device)
         fn = self._lib.b200nufft_interp_modulated if modulated else self._lib.b200nufft_interp
-        _lib.check(fn(self._plan, _ptr(store), _ptr(y), nb, _stream()))
+        _lib.check(fn(self._plan, _ptr(store), _ptr(y), nb, self._stream()))
         return y
 
     def _y2k_device(self, y, modulated=False):
@@ -247,7 +256,7 @@ class NUFFT:
         nb = self._nb_of(y, 1, 'y')
         view, store = self._new_grid(nb, y.dim() == 2)
         fn = self._lib.b200nufft_gridding_modulated if modulated else self._lib.b200nufft_gridding
-        _lib.check(fn(self._plan, _ptr(y), _ptr(store), nb, _stream()))
+        _lib.check(fn(self._plan, _ptr(y), _ptr(store), nb, self._stream()))
         return view
 
     def _kspace_modulated(self):
@@ -262,8 +271,8 @@ class NUFFT:
         self._require_plan()
         store, nb, batched = self._grid_storage(k)
         xx = torch.empty(tuple(self.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=self.device)
-        _lib.check(self._lib.b200nufft_fft(self._plan, _ptr(store), nb, 1, _stream()))
-        _lib.check(self._lib.b200nufft_crop_scale(self._plan, _ptr(store), _ptr(xx), nb, 0, 0, None, _stream()))
+        _lib.check(self._lib.b200nufft_fft(self._plan, _ptr(store), nb, 1, self._stream()))
+        _lib.check(self._lib.b200nufft_crop_scale(self._plan, _ptr(store), _ptr(xx), nb, 0, 0, None, self._stream()))
         return xx
 
     def _forward_device(self, gx):
@@ -272,7 +281,7 @@ class NUFFT:
         nb = self._nb_of(gx, self.ndims, 'x')
         y = torch.empty((self.M, nb) if gx.dim() == self.ndims + 1 else (self.M,), dtype=torch.complex64,
                         device=self.device)
-        _lib.check(self._lib.b200nufft_forward(self._plan, _ptr(gx), _ptr(y), nb, _stream()))
+        _lib.check(self._lib.b200nufft_forward(self._plan, _ptr(gx), _ptr(y), nb, self._stream()))
         return y
 
     def _adjoint_device(self, gy):
@@ -280,7 +289,7 @@ class NUFFT:
         gy = self._check_dev(gy, (self.M,), 'y')
         nb = self._nb_of(gy, 1, 'y')
         x = torch.empty(tuple(self.Nd) + ((nb,) if gy.dim() == 2 else ()), dtype=torch.complex64, device=self.device)
-        _lib.check(self._lib.b200nufft_adjoint(self._plan, _ptr(gy), _ptr(x), nb, _stream()))
+        _lib.check(self._lib.b200nufft_adjoint(self._plan, _ptr(gy), _ptr(x), nb, self._stream()))
         return x
 
     def _selfadjoint_device(self, gx):
@@ -298,9 +307,9 @@ class NUFFT:
             ones = torch.ones((self.M,), dtype=torch.complex64, device=self.device)
             self._W = self._xx2k_device(self._adjoint_device(ones)).abs().to(torch.complex64).contiguous()
         k = self._xx2k_device(gx).contiguous()
-        _lib.check(self._lib.b200nufft_cmul(_ptr(k), _ptr(self._W), k.numel(), _stream()))
+        _lib.check(self._lib.b200nufft_cmul(_ptr(k), _ptr(self._W), k.numel(), self._stream()))
         x2 = torch.empty(tuple(self.Nd), dtype=torch.complex64, device=self.device)
-        _lib.check(self._lib.b200nufft_ifft_crop(self._plan, _ptr(k), _ptr(x2), 1, 0, 0, None, _stream()))
+        _lib.check(self._lib.b200nufft_ifft_crop(self._plan, _ptr(k), _ptr(x2), 1, 0, 0, None, self._stream()))
         return x2
 
     def _solve_device(self, gy, solver=None, *args, **kwargs):
@@ -347,7 +356,7 @@ class NUFFT:
             raise ValueError('s must have shape Nd')
         y = torch.empty((self.M, self.batch), dtype=torch.complex64, device=self.device)
         sens = _ptr(self._sense) if self._sense is not None else None
-        _lib.check(self._lib.b200nufft_forward_one2many(self._plan, _ptr(gs), sens, _ptr(y), self.batch, _stream()))
+        _lib.check(self._lib.b200nufft_forward_one2many(self._plan, _ptr(gs), sens, _ptr(y), self.batch, self._stream()))
         return self.to_host(y) if host else y
 
     def adjoint_many2one(self, y):
@@ -357,7 +366,7 @@ class NUFFT:
         gy = self._check_dev(gy, (self.M, self.batch), 'y')
         s = torch.empty(tuple(self.Nd), dtype=torch.complex64, device=self.device)
         sens = _ptr(self._sense) if self._sense is not None else None
-        _lib.check(self._lib.b200nufft_adjoint_many2one(self._plan, _ptr(gy), sens, _ptr(s), self.batch, _stream()))
+        _lib.check(self._lib.b200nufft_adjoint_many2one(self._plan, _ptr(gy), sens, _ptr(s), self.batch, self._stream()))
         return self.to_host(s) if host else s
 
     def selfadjoint_one2many2one(self, s):
@@ -394,11 +403,11 @@ class NUFFT:
         y = self._host_out(out, (self.M, nb) if x.ndim == self.ndims + 1 else (self.M,), 'out')
         with torch.cuda.device(self.device):
             if slot is None:
-                _lib.check(self._lib.b200nufft_forward_host(self._plan, x.ctypes.data, y.ctypes.data, nb, _stream()))
+                _lib.check(self._lib.b200nufft_forward_host(self._plan, x.ctypes.data, y.ctypes.data, nb, self._stream()))
             else:
                 self._inflight[(0, int(slot))] = (x, y)      # keep the host arrays alive until wait()
                 _lib.check(self._lib.b200nufft_forward_host_async(self._plan, x.ctypes.data, y.ctypes.data, nb,
-                                                                  int(slot), _stream()))
+                                                                  int(slot), self._stream()))
         return y
 
     def adjoint(self, y, out=None, slot=None):
@@ -409,11 +418,11 @@ class NUFFT:
         x = self._host_out(out, tuple(self.Nd) + ((nb,) if y.ndim == 2 else ()), 'out')
         with torch.cuda.device(self.device):
             if slot is None:
-                _lib.check(self._lib.b200nufft_adjoint_host(self._plan, y.ctypes.data, x.ctypes.data, nb, _stream()))
+                _lib.check(self._lib.b200nufft_adjoint_host(self._plan, y.ctypes.data, x.ctypes.data, nb, self._stream()))
             else:
                 self._inflight[(1, int(slot))] = (y, x)
                 _lib.check(self._lib.b200nufft_adjoint_host_async(self._plan, y.ctypes.data, x.ctypes.data, nb,
-                                                                  int(slot), _stream()))
+                                                                  int(slot), self._stream()))
         return x
 
     def wait(self, op, slot):
@@ -462,10 +471,10 @@ class NUFFT:
         k0 = torch.empty((self.M, self.ndims), dtype=torch.int32, device=dev)
         perm = torch.empty((self.M,), dtype=torch.int32, device=dev)
         tile = numpy.zeros(2 * self.ndims, dtype=numpy.int32)
-        _lib.check(self._lib.b200nufft_plan_get_kindx(self._plan, _ptr(kindx), _stream()))
-        _lib.check(self._lib.b200nufft_plan_get_udata(self._plan, _ptr(udata), _stream()))
-        _lib.check(self._lib.b200nufft_plan_get_k0(self._plan, _ptr(k0), _stream()))
-        _lib.check(self._lib.b200nufft_plan_get_perm(self._plan, _ptr(perm), _stream()))
+        _lib.check(self._lib.b200nufft_plan_get_kindx(self._plan, _ptr(kindx), self._stream()))
+        _lib.check(self._lib.b200nufft_plan_get_udata(self._plan, _ptr(udata), self._stream()))
+        _lib.check(self._lib.b200nufft_plan_get_k0(self._plan, _ptr(k0), self._stream()))
+        _lib.check(self._lib.b200nufft_plan_get_perm(self._plan, _ptr(perm), self._stream()))
         _lib.check(self._lib.b200nufft_plan_get_tile(self._plan, tile.ctypes.data))
         return (kindx.cpu().numpy().view(numpy.uint32), udata.cpu().numpy(), k0.cpu().numpy(), perm.cpu().numpy(),
                 tuple(int(v) for v in tile[:self.ndims]), tuple(int(v) for v in tile[self.ndims:]))
@@ -475,7 +484,7 @@ class NUFFT:
         self._require_plan()
         perm = torch.empty((self.M,), dtype=torch.int32, device=self.device)
         tile = numpy.zeros(6, dtype=numpy.int32)
-        _lib.check(self._lib.b200nufft_plan_get_col_perm(self._plan, _ptr(perm), tile.ctypes.data, _stream()))
+        _lib.check(self._lib.b200nufft_plan_get_col_perm(self._plan, _ptr(perm), tile.ctypes.data, self._stream()))
         return perm.cpu().numpy(), tuple(int(v) for v in tile[:3]), tuple(int(v) for v in tile[3:])
 
     def layout(self):

@@ -22,8 +22,8 @@ def _ptr(t):
     return _vp(t.data_ptr())
 
 
-def _stream():
-    return _vp(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
 
 
 class CudaVectorOps:
@@ -37,19 +37,19 @@ class CudaVectorOps:
         return torch.zeros(6, dtype=torch.float64, device=device)
 
     def cg_init(self, b, Ax, r, p, rsold):
-        _lib.check(self.L.b200nufft_cg_init(_ptr(b), _ptr(Ax), _ptr(r), _ptr(p), _ptr(rsold), r.numel(), _stream()))
+        _lib.check(self.L.b200nufft_cg_init(_ptr(b), _ptr(Ax), _ptr(r), _ptr(p), _ptr(rsold), r.numel(), _stream(r.device)))
 
     def dotc(self, a, b, out):
         out.zero_()
-        _lib.check(self.L.b200nufft_dotc(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()))
+        _lib.check(self.L.b200nufft_dotc(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream(a.device)))
 
     def update_xr(self, x, r, p, Ap, rsold, pAp, rsnew):
         rsnew.zero_()
         _lib.check(self.L.b200nufft_cg_update_xr(_ptr(x), _ptr(r), _ptr(p), _ptr(Ap), _ptr(rsold), _ptr(pAp),
-                                                 _ptr(rsnew), x.numel(), _stream()))
+                                                 _ptr(rsnew), x.numel(), _stream(x.device)))
 
     def update_p(self, p, r, rsnew, rsold):
-        _lib.check(self.L.b200nufft_cg_update_p(_ptr(p), _ptr(r), _ptr(rsnew), _ptr(rsold), p.numel(), _stream()))
+        _lib.check(self.L.b200nufft_cg_update_p(_ptr(p), _ptr(r), _ptr(rsnew), _ptr(rsold), p.numel(), _stream(p.device)))
 
 
 def cg_kspace(G, b, maxiter, ops, allreduce=None):
@@ -106,7 +106,7 @@ def cg(nufft, gy, maxiter=30, group=None):
     # inverse FFT, crop, divide by sn  (solve_device.py:463-480)
     x2 = torch.empty(tuple(nufft.Nd) + ((nb,) if batched else ()), dtype=torch.complex64, device=nufft.device)
     crop = L.b200nufft_ifft_crop_modulated if mod else L.b200nufft_ifft_crop
-    _lib.check(crop(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, _stream()))
+    _lib.check(crop(nufft._plan, _ptr(xs), _ptr(x2), nb, 2, 0, None, nufft._stream()))
     return x2
 
 
@@ -145,7 +145,7 @@ def L1TVOLS(nufft, gy, maxiter, rho):
     AH = nufft.adjoint_many2one if multi else nufft._adjoint_device
     AHA = nufft.selfadjoint_one2many2one if multi else nufft._selfadjoint_device
     L = nufft._lib
-    st = _stream
+    st = nufft._stream
     mu = 1.0
     LMBD = rho * mu
     nd = nufft.ndims
@@ -210,7 +210,7 @@ def krylov(nufft, gy, solver, *args, **kwargs):
     ks = dev(vec, Kd)
     x2 = torch.empty(tuple(nufft.Nd), dtype=torch.complex64, device=nufft.device)
     _lib.check(nufft._lib.b200nufft_ifft_crop(nufft._plan, _ptr(nufft._grid_storage(ks)[0]), _ptr(x2), 1, 2, 0, None,
-                                              _stream()))
+                                              nufft._stream()))
     return x2
 
 

@@ -25,3 +25,12 @@ def golden(request):
     g['Kd'] = tuple(int(v) for v in g['Kd'])
     g['Jd'] = tuple(int(v) for v in g['Jd'])
     return g
+
+
+def load_golden(name):
+    """a golden file by name (the size / multi-coil fixtures are not part of the parametrised `golden` fixture)"""
+    import numpy
+    g = dict(numpy.load(os.path.join(GOLDEN, name + '.npz')))
+    for k in ('Nd', 'Kd', 'Jd'):
+        g[k] = tuple(int(v) for v in g[k])
+    return g

@@ -144,6 +144,22 @@ class MockDeviceNUFFT:
     def _selfadjoint_device(self, x):
         return garr(self._cpu._adjoint_cpu(self._cpu._forward_cpu(numpy.asarray(x))).astype(c64))
 
+    # the method names linalg/solve_hsa.py uses (NUFFT_hsa API)
+    def y2k(self, y):
+        return self._y2k_device(y)
+
+    def xx2k(self, xx):
+        return self._xx2k_device(xx)
+
+    def k2xx(self, k):
+        return self._k2xx_device(k)
+
+    def adjoint(self, y):
+        return self._adjoint_device(y)
+
+    def selfadjoint(self, x):
+        return self._selfadjoint_device(x)
+
 
 def install_fake_reikna():
     """solve_device.solve('cg') does `from reikna.algorithms import Reduce, Predicate, predicate_sum`."""
@@ -204,6 +220,9 @@ def run_case(name, om, Nd, Kd, Jd, seed, solvers=False):
         out['solve_y'] = y
         out['cg10'] = numpy.asarray(solve_device.solve(dev, garr(y), 'cg', maxiter=10)).astype(c64)
         out['l1tvols5'] = numpy.asarray(solve_device.solve(dev, garr(y), 'L1TVOLS', maxiter=5, rho=2)).astype(c64)
+        # L1TVLAD only exists in the batched twin (linalg/solve_hsa.py:74-274); run single-coil on the same mock
+        from reference.linalg import solve_hsa
+        out['l1tvlad5'] = numpy.asarray(solve_hsa.L1TVLAD(dev, garr(y), 5, 2)).astype(c64)
         from reference.linalg import solve_cpu
         out['dc2'] = numpy.asarray(solve_cpu.solve(A, y, 'dc', 2)).astype(c64)       # linalg/solve_cpu.py:165-225
         # scipy Krylov family of the CPU solve (linalg/solve_cpu.py:226-288), few iterations, fixed counts

@@ -475,8 +475,15 @@ def laplacian_kernel(Kd):
     return numpy.fft.fftn(uker)
 
 
-def solve_l1tvols(nufft, y, maxiter, rho):
+def solve_l1tvlad(nufft, y, maxiter, rho):
+    """linalg/solve_hsa.py:74-274: L1TVOLS plus a second split variable for the data term (least absolute deviation)."""
+    return solve_l1tvols(nufft, y, maxiter, rho, lad=True)
+
+
+def solve_l1tvols(nufft, y, maxiter, rho, lad=False):
     """linalg/solve_device.py:74-275 (split-Bregman TV, device variant).
+    lad=True: the L1TVLAD variant of the batched twin (linalg/solve_hsa.py:74-274): rhs uses AHyk + df - bf (:134-138),
+    df = shrink(zf + bf, 1/mu) and bf += zf - df after the TV shrinkage (:229-260).
 
     Multi-coil data y (M, B) on a batch operator: the same iteration with the closures of the batched twin
     (linalg/solve_hsa.py:275-476, AHA = nufft.selfadjoint, AH = nufft.adjoint at :282-287) acting between the ONE image
@@ -508,8 +515,10 @@ def solve_l1tvols(nufft, y, maxiter, rho):
         return numpy.fft.fftn(out).astype(c64)
 
     thr = numpy.float32(1.0 / LMBD)
+    thr_f = numpy.float32(1.0 / mu)
+    bf, df = z.copy(), z.copy()
     for _ in range(maxiter):
-        rhs = (c64(mu) * AHyk).astype(c64)
+        rhs = (c64(mu) * ((AHyk + df).astype(c64) - bf).astype(c64) if lad else c64(mu) * AHyk).astype(c64)
         for pp in range(nd):
             rhs = (rhs + c64(LMBD) * Dt((dd[pp] - bb[pp]).astype(c64), pp)).astype(c64)
         k = (pad_fft(rhs) / uker).astype(c64)
@@ -529,6 +538,12 @@ def solve_l1tvols(nufft, y, maxiter, rho):
         for pp in range(nd):
             dd[pp] = (s_tmp[pp] * t).astype(c64)
             bb[pp] = (bb[pp] + (zz[pp] - dd[pp])).astype(c64)
+        if lad:
+            tf = (zf + bf).astype(c64)
+            fr, fi = tf.real, tf.imag
+            df = (((fr > thr_f) * (fr - thr_f) + (fr < -thr_f) * (fr + thr_f)) +
+                  1j * ((fi > thr_f) * (fi - thr_f) + (fi < -thr_f) * (fi + thr_f))).astype(c64)
+            bf = (bf + (zf - df)).astype(c64)
         AHyk = (AHyk - zf).astype(c64)
     return xkp1
 

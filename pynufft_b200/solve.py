@@ -130,7 +130,19 @@ def _laplacian_kernel(nufft):
     return numpy.fft.fftn(uker)
 
 
-def L1TVOLS(nufft, gy, maxiter, rho):
+def L1TVLAD(nufft, gy, maxiter, rho):
+    """L1-TV regularised least absolute deviation (linalg/solve_hsa.py:74-274): L1TVOLS with a second
+    split variable on the data term: rhs from AHyk + df - bf, df = shrink(zf + bf, 1/mu), bf += zf - df."""
+    return L1TVOLS(nufft, gy, maxiter, rho, lad=True)
+
+
+def _aniso_shrink(t, thr):
+    """cAnisoShrink (re_subroutine.py:973-993): soft threshold on the real and imaginary parts separately"""
+    v = torch.view_as_real(t)
+    return torch.view_as_complex(torch.where(v > thr, v - thr, torch.where(v < -thr, v + thr, torch.zeros_like(v))))
+
+
+def L1TVOLS(nufft, gy, maxiter, rho, lad=False):
     """Split-Bregman total variation, device variant (solve_device.py:74-275).
 
     Multi-coil data (M, B) on a batch plan: the batched twin's closures (linalg/solve_hsa.py:275-476, AHA =
@@ -161,14 +173,21 @@ def L1TVOLS(nufft, gy, maxiter, rho):
     bb = torch.zeros((nd,) + Nd, dtype=torch.complex64, device=dev)
     rhs = torch.empty(Nd, dtype=torch.complex64, device=dev)
     k = torch.empty(tuple(nufft.Kd), dtype=torch.complex64, device=dev)
+    bf = torch.zeros(Nd, dtype=torch.complex64, device=dev) if lad else None
+    df = torch.zeros(Nd, dtype=torch.complex64, device=dev) if lad else None
     for _ in range(int(maxiter)):
-        _lib.check(L.b200nufft_tv_rhs(nufft._plan, _ptr(AHyk), _ptr(dd), _ptr(bb), mu, LMBD, _ptr(rhs), st()))
+        src = ((AHyk + df) - bf).contiguous() if lad else AHyk           # solve_hsa.py:134-138
+        _lib.check(L.b200nufft_tv_rhs(nufft._plan, _ptr(src), _ptr(dd), _ptr(bb), mu, LMBD, _ptr(rhs), st()))
         # xkp1 = k2xx(xx2k(rhs) / uker): zero-pad + FFT without sn scaling (:174-181)
         _lib.check(L.b200nufft_pad_fft(nufft._plan, _ptr(rhs), _ptr(k), 1, 0, 0, None, st()))
         _lib.check(L.b200nufft_cdiv(_ptr(k), _ptr(uker), k.numel(), st()))
         _lib.check(L.b200nufft_ifft_crop(nufft._plan, _ptr(k), _ptr(xkp1), 1, 0, 0, None, st()))
         zf = AHA(xkp1)
         _lib.check(L.b200nufft_tv_shrink(nufft._plan, _ptr(xkp1), _ptr(dd), _ptr(bb), LMBD, st()))
+        if lad:                                                           # solve_hsa.py:229-260 (zf there = AHA x - AHy)
+            zfm = zf - AHy
+            df = _aniso_shrink(zfm + bf, 1.0 / mu)
+            bf = bf + (zfm - df)
         _lib.check(L.b200nufft_tv_bregman(_ptr(AHyk), _ptr(zf), _ptr(AHy), n, st()))
     return xkp1
 
@@ -224,6 +243,8 @@ def solve(nufft, gy, solver=None, maxiter=30, *args, **kwargs):
         return cg(nufft, gy, maxiter=maxiter, **kwargs)
     if solver == 'L1TVOLS':
         return L1TVOLS(nufft, gy, maxiter=maxiter, *args, **kwargs)
+    if solver == 'L1TVLAD':
+        return L1TVLAD(nufft, gy, maxiter=maxiter, *args, **kwargs)
     if solver == 'dc':
         return density_compensation(nufft, gy, maxiter=maxiter)
-    raise ValueError("solver must be 'cg', 'L1TVOLS', 'dc' or one of %s (got %r)" % (', '.join(KRYLOV), solver))
+    raise ValueError("solver must be 'cg', 'L1TVOLS', 'L1TVLAD', 'dc' or one of %s (got %r)" % (', '.join(KRYLOV), solver))

@@ -94,6 +94,7 @@ def test_solvers_match_reference_device_algorithms(golden, dev):
     y = golden['solve_y']
     assert rel(A.solve(y, 'cg', maxiter=10), golden['cg10']) < 1e-4
     assert rel(A.solve(y, 'L1TVOLS', maxiter=5, rho=2), golden['l1tvols5']) < 1e-4
+    assert rel(A.solve(y, 'L1TVLAD', maxiter=5, rho=2), golden['l1tvlad5']) < 1e-4
     assert rel(A.solve(y, 'dc', maxiter=2), golden['dc2']) < 1e-4
     # the CPU solve's scipy Krylov family driving the device operator
     assert rel(A.solve(y, 'lsmr', maxiter=6), golden['lsmr6']) < 1e-4
@@ -528,12 +529,12 @@ def test_config4_solvers(c2, dev):
     L1TVOLS (TV-SENSE) and single-coil L1TVOLS against the oracle."""
     A, O, s = c2
     y = O.forward_one2many(s).astype(numpy.complex64)
-    # The radial 32-coil k-space system is ill-conditioned: float32 CG amplifies rounding (the complex64 restatement of
-    # the device arithmetic, orc.solve_cg(..., complex64), drifts from the exact iterates by 2.3e-1 after 10 and 1.5e-2
-    # after 100 iterations).  Parity is therefore judged against the exact-arithmetic (complex128) iterates of the same
-    # algorithm, stored by oracle/make_cg_fixture.py at 60 000 entries (tests/golden/c4_cg_c128.npz).  The CUDA solver
-    # keeps the CG scalars in float64 on the device and is far closer to the exact iterates than the complex64
-    # restatement; the bounds below are 4x what it measured on B200 (printed).
+    # The radial 32-coil k-space system is ill-conditioned: storing the CG vectors in complex64 moves the iterates away
+    # from the exact (complex128) ones by 2.3e-1 after 10 and 1.5e-2 after 100 iterations -- deterministically: the CUDA
+    # solver and the numpy restatement of the device arithmetic (orc.solve_cg, pinned to the reference's own
+    # solve_device.py by the cg10 goldens) round at the same places and follow the same perturbed trajectory.  Parity is
+    # agreement with that restatement; both runs are stored by oracle/make_cg_fixture.py at 60 000 entries of the result
+    # (tests/golden/c4_cg_c128.npz; the 100-iteration CPU runs take minutes).  Bounds: 4x what B200 measured (printed).
     import os
     from conftest import GOLDEN
     fx = dict(numpy.load(os.path.join(GOLDEN, 'c4_cg_c128.npz')))
@@ -541,13 +542,16 @@ def test_config4_solvers(c2, dev):
     x10 = A.solve(y, 'cg', maxiter=10)
     x100 = A.solve(y, 'cg', maxiter=100)             # README: solve('cg', maxiter=100)
     assert numpy.all(numpy.isfinite(x10)) and numpy.all(numpy.isfinite(x100))
-    e10 = rel(x10.ravel()[pick], fx['x10'])
-    e100 = rel(x100.ravel()[pick], fx['x100'])
-    n10 = abs(numpy.linalg.norm(x10) - float(fx['norm10'])) / float(fx['norm10'])
-    n100 = abs(numpy.linalg.norm(x100) - float(fx['norm100'])) / float(fx['norm100'])
-    print('config-4 CG vs exact iterates: 10 it %.3e (norm %.1e), 100 it %.3e (norm %.1e)' % (e10, n10, e100, n100))
-    assert e10 < CG10_BOUND and e100 < CG100_BOUND, (e10, e100)
-    assert n10 < CG10_BOUND and n100 < CG100_BOUND
+    e10, e100 = rel(x10.ravel()[pick], fx['x10_c64']), rel(x100.ravel()[pick], fx['x100_c64'])
+    n10 = abs(numpy.linalg.norm(x10) - float(fx['norm10_c64'])) / float(fx['norm10_c64'])
+    n100 = abs(numpy.linalg.norm(x100) - float(fx['norm100_c64'])) / float(fx['norm100_c64'])
+    x10e, x100e = rel(x10.ravel()[pick], fx['x10']), rel(x100.ravel()[pick], fx['x100'])
+    print('config-4 CG vs complex64 restatement: 10 it %.3e (norm %.1e), 100 it %.3e (norm %.1e); vs exact iterates: '
+          '%.3e, %.3e (restatement vs exact: %.3e, %.3e)' % (e10, n10, e100, n100, x10e, x100e,
+                                                             rel(fx['x10_c64'], fx['x10']), rel(fx['x100_c64'], fx['x100'])))
+    assert e10 < CG10_BOUND and n10 < CG10_BOUND, (e10, n10)
+    assert e100 < CG100_BOUND and n100 < CG100_BOUND, (e100, n100)
+    assert x100e < 2 * rel(fx['x100_c64'], fx['x100'])      # no further from exact arithmetic than the restatement is
     # multi-coil L1TVOLS (TV-SENSE closures: AH = adjoint_many2one, AHA = selfadjoint_one2many2one,
     # linalg/solve_hsa.py:275-476 with :282-287 on the batch operator) at configuration-4 size
     xl = A.solve(y, 'L1TVOLS', maxiter=5, rho=2)

@@ -206,6 +206,11 @@ int b200nufft_set_variant(b200nufft_plan_t plan, int interp_variant, int griddin
  * permutation (device pointer, M entries; may be NULL) and its sort key as (tile, sub-tile) edges of the generic
  * bin key (host pointer, 6 entries; may be NULL): tile = (K0, 4, 5), sub-tile = (1, 4, 5).                      */
 int b200nufft_set_layout_preference(int pref);
+/* Grid layout of the stage entry points (scale_pad, fft, interp, gridding, crop_scale, pad_fft, ifft_crop) for a call
+ * with nb coils: 0 = coil-major (nb contiguous Kd grids), 1 = batch-innermost (k[K0][K1][nb], the reference's own
+ * Kd + (batch,) order, linalg/nufft_hsa.py:225-227).  2-D Jd = 6^2 plans use 1 for even nb >= 8 (csrc/sweep2d.cu:
+ * coil on the lanes, register-resident row sweep, strided-batch cuFFT); images and data are batch-innermost always. */
+int b200nufft_grid_layout(b200nufft_plan_t plan, int nb);
 int b200nufft_plan_get_layout(b200nufft_plan_t plan);
 int b200nufft_plan_get_col_perm(b200nufft_plan_t plan, int32_t* perm, int32_t* tile_host, void* stream);
 /* The column-sweep kernel produces the phase-modulated grid G'[g] = G[g] * prod_d exp(i gam_d (N_d - 1)/2 * g_d),

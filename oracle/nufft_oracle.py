@@ -252,6 +252,9 @@ def column_sweep_tiles(Kd, Jd):
     with tile = (K0, 4, 5), sub-tile = (1, 4, 5)."""
     if (len(Kd) == 3 and tuple(Jd) == (6, 6, 6) and Kd[0] >= 6 and Kd[1] >= 9 and Kd[2] >= 10):
         return (int(Kd[0]), 4, 5), (1, 4, 5)
+    # 2-D multi-coil row sweep (csrc/sweep2d.cu sweep2d_supported): key = strip(3 columns) * K0 + first row
+    if (len(Kd) == 2 and tuple(Jd) == (6, 6) and Kd[0] >= 16 and Kd[1] >= 8):
+        return (int(Kd[0]), 3), (1, 3)
     return None
 
 

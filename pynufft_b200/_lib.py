@@ -53,6 +53,7 @@ SIGNATURES = {
     'b200nufft_set_variant': (_i, [_vp, _i, _i]),
     'b200nufft_set_layout_preference': (_i, [_i]),
     'b200nufft_plan_get_layout': (_i, [_vp]),
+    'b200nufft_grid_layout': (_i, [_vp, _i]),
     'b200nufft_plan_get_col_perm': (_i, [_vp, _vp, _vp, _vp]),
     'b200nufft_gridding_is_modulated': (_i, [_vp]),
     'b200nufft_kspace_modulated': (_i, [_vp]),

@@ -127,6 +127,9 @@ struct PlanConst {
 // column-sweep gridding (col3d.cu): 4 x 5 cross-section columns of first-neighbour cells swept along dim 0;
 // 32-word sample records in sweep order
 constexpr int COL_T1 = 4, COL_T2 = 5, COL_RECW = 32, COL_SEG = 320;
+// 2-D multi-coil row sweep (sweep2d.cu): strips of SW2_CT first-neighbour columns (dim 1) swept along dim 0, coil on the
+// lanes; 20-word sample records in sweep order
+constexpr int SW2_CT = 3, SW2_RECW = 20, SW2_SEG = 64;
 
 struct WorkItem {   // one launch unit of the tiled kernels: samples [begin, end) of one tile
     int tile;
@@ -160,6 +163,16 @@ struct b200nufft_plan_s {
     float4* d_cside = nullptr;      // (M,) (P''.re, P''.im, original index, 0) in sweep order
     WorkItem* d_cwork = nullptr;    // (column, begin, end) segments of at most COL_SEG samples
     int n_cwork = 0;
+    // 2-D multi-coil row sweep (2-D, J = 6; sweep2d.cu): samples sorted by (strip, first row), batch-innermost grids
+    bool has_sw2 = false;
+    int* d_sw_perm = nullptr;       // (M,) sweep-order permutation (parity export)
+    float* d_sw_rec = nullptr;      // (M, SW2_RECW)
+    WorkItem* d_sw_work = nullptr;  // (strip, begin, end) segments of at most SW2_SEG samples
+    int n_sw_work = 0;
+    cufftHandle fft_bi = 0;         // strided-batch cuFFT plan for the batch-innermost grid layout
+    int fft_bi_nb = 0;
+    bool fft_bi_valid = false;
+    bool attr_sw2 = false;
     int* d_ccount = nullptr;        // per-coil work counters of the persistent column kernels
     int ccount_nb = 0;
     int n_sm = 0;
@@ -175,6 +188,8 @@ struct b200nufft_plan_s {
     // scratch grids for the compositions
     float2* d_grid = nullptr;
     int grid_nb = 0;
+    float2* d_grid2 = nullptr;      // coil-major FFT scratch of the batch-innermost 2-D path (sweep2d.cu)
+    int grid2_nb = 0;
     // host staging for the *_host entry points
     float2* d_xin = nullptr;
     float2* d_yio = nullptr;
@@ -199,15 +214,16 @@ struct b200nufft_plan_s {
     float2* d_tw256 = nullptr;
     float2* d_xc = nullptr;         // per-coil image scratch for many2one
     int xc_nb = 0;
-    bool attr_b2d = false, attr_grid = false, attr_interp = false, attr_col = false;   // cudaFuncSetAttribute done on this plan's device
+    bool attr_grid = false, attr_interp = false, attr_col = false;   // cudaFuncSetAttribute done on this plan's device
     int interp_variant = 0, gridding_variant = 0, fft_variant = 0;   // 0 auto, 1 generic / cuFFT, 2 tiled, 3 column sweep (interp)
     long long bytes = 0;
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-bool batch2d_supported(const Geom& g, int nb);
+// 2-D calls with an even number (>= 8) of coils run on BATCH-INNERMOST grids, k[K0][K1][nb] (the reference's own layout,
+// linalg/nufft_hsa.py:225-227), with the coil on the lanes (sweep2d.cu); every other call keeps coil-major grids
 static inline bool use_bi(const b200nufft_plan_s* p, int nb) {
-    return p->interp_variant != 1 && p->gridding_variant != 1 && batch2d_supported(p->g, nb);
+    return p->has_sw2 && p->interp_variant != 1 && p->gridding_variant != 1 && nb >= 8 && (nb & 1) == 0;
 }
 
 // tiled kernels (interp_tiled.cu / grid_tiled.cu); return B200_ERR_UNSUPPORTED if geometry does not fit
@@ -216,6 +232,7 @@ int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int n
 int gridding_tiled_launch(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
 bool tiled_supported(const Geom& g);
 int ensure_scratch(b200nufft_plan_t p, int nb);
+int ensure_scratch2(b200nufft_plan_t p, int nb);
 // col3d.cu: register-resident column-sweep gridding (3-D, J = 6); the grid it produces is phase-modulated
 bool col3d_supported(const Geom& g);
 // zeroes the grid itself (inside its pre-pass kernel)
@@ -252,10 +269,18 @@ int combine_coils(const float2* xc, const float2* sens, float2* s, long long N, 
 bool single2d_supported(const Geom& g);
 int single2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
 int single2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
-// batch2d.cu: 2-D multi-coil kernels with the coil on the lanes (grids stay coil-major)
-bool batch2d_supported(const Geom& g, int nb);
-int batch2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st);
-int batch2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
+// sweep2d.cu: 2-D multi-coil kernels with the coil on the lanes, register-resident row sweep, batch-innermost grids
+bool sweep2d_supported(const Geom& g);
+int sweep2d_interp(b200nufft_plan_t p, const float2* grid_bi, float2* y, int nb, cudaStream_t st);
+int sweep2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_bi, int nb, cudaStream_t st);   // zero-fills
+int sweep2d_scale_pad(b200nufft_plan_t p, const float2* x, float2* grid_bi, int nb, int apply_sn, int x_single,
+                      const float2* sens, cudaStream_t st);
+int sweep2d_crop_scale(b200nufft_plan_t p, const float2* grid_bi, float2* x, int nb, int mode, int combine,
+                       const float2* sens, float scale, cudaStream_t st);
+int sweep2d_fft(b200nufft_plan_t p, float2* grid_bi, int nb, int inverse, cudaStream_t st);
+int sweep2d_pad_fft(b200nufft_plan_t p, const float2* x, float2* grid_bi, int nb, int apply_sn, int x_single,
+                    const float2* sens, cudaStream_t st);
+int sweep2d_ifft_to_scratch(b200nufft_plan_t p, const float2* grid_bi, int nb, cudaStream_t st);   // coil-major result in p->d_grid2
 
 
 // ---- small device helpers ---------------------------------------------------------------

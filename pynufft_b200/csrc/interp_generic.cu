@@ -111,7 +111,7 @@ int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaS
         if (interp_uses_col(p)) return col3d_interp(p, grid, y, nb, st);
         return interp_tiled_launch(p, grid, y, nb, st, true);
     }
-    if (use_bi(p, nb)) return batch2d_interp(p, grid, y, nb, st);
+    if (use_bi(p, nb)) return sweep2d_interp(p, grid, y, nb, st);             // batch-innermost grid
     if (p->interp_variant != 1 && single2d_supported(p->g)) return single2d_interp(p, grid, y, nb, st);
     if (interp_uses_col(p)) {
         // true grid in: one modulation pass into the plan's scratch, then the column-sweep gather
@@ -140,9 +140,9 @@ int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cud
         if (rc || modulated_ok) return rc;
         return col3d_demodulate(p, grid, nb, st);
     }
+    if (p->M > 0 && use_bi(p, nb)) return sweep2d_gridding(p, y, grid, nb, st);   // batch-innermost grid, zero-fills
     CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
     if (p->M == 0) return B200_OK;
-    if (use_bi(p, nb)) return batch2d_gridding(p, y, grid, nb, st);
     if (p->gridding_variant != 1 && single2d_supported(p->g)) return single2d_gridding(p, y, grid, nb, st);
     if (p->gridding_variant != 1 && tiled_supported(p->g)) return gridding_tiled_launch(p, y, grid, nb, st);
     if (p->gridding_variant == 2) {

@@ -198,6 +198,62 @@ __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const do
     side[i] = make_float4((float)cs, (float)sn, __int_as_float(m), 0.f);
 }
 
+// ---- 2-D multi-coil row sweep (sweep2d.cu): key = (strip, first row), 20-word records in sweep order ----
+// A strip is SW2_CT first-neighbour columns (dim 1) wide; its box is 8 columns.
+// record words: [c0[0..3] | c0[4] c0[5] p0 run | c1t[0..3] | c1t[4..7] | P''.re P''.im m 0]
+//   c0[j]: weight of row p0 + j;  c1t[b] = c1[b - k1rel] (zero outside the footprint): box columns
+//   run: samples from this one to the end of its (strip, first row) bin
+//   weights of neighbours that wrap around the periodic grid carry (-1)^(N_d - 1) (phase-modulated grid)
+//   P'' = prod_d exp(i (om N/2 - s dk - s (k0' - 1))), m = original sample index
+__global__ void k_sw2_keys(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om, long long M,
+                           int* __restrict__ keys, int* __restrict__ vals) {
+    long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    int ks[2];
+    for (int d = 0; d < 2; ++d) {
+        double q;
+        ks[d] = wrap_index(offset_k0(om[m * 2 + d], pc->gam[d], g.J[d], &q) + 1, g.K[d]);
+    }
+    keys[m] = (ks[1] / SW2_CT) * g.K[0] + ks[0];
+    vals[m] = (int)m;
+}
+
+__global__ void k_sw2_records(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om,
+                              const int* __restrict__ perm, long long M, const int* __restrict__ cbin,
+                              float* __restrict__ rec) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int m = perm[i];
+    float* out = rec + i * SW2_RECW;
+    int* outi = reinterpret_cast<int*>(out);
+    for (int w = 0; w < SW2_RECW; ++w) out[w] = 0.f;
+    double ph = 0.0;
+    int ks[2];
+    for (int d = 0; d < 2; ++d) {
+        DimResult R;
+        const double o = om[(long long)m * 2 + d];
+        dim_math(o, d, g, pc, R);
+        const int k = wrap_index(R.k0 + 1, g.K[d]);
+        ks[d] = k;
+        const float sgd = ((g.N[d] - 1) & 1) ? -1.f : 1.f;
+        for (int j = 0; j < 6; ++j) {
+            const float cj = (k + j >= g.K[d]) ? sgd * (float)R.c[j] : (float)R.c[j];
+            if (d == 0) out[j] = cj;                       // words 0..5
+            else out[8 + k % SW2_CT + j] = cj;             // box column 0..7
+        }
+        const double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+        ph += o * (double)g.N[d] / 2.0 - s * R.dk - s * (double)(k - 1);
+    }
+    const int key = (ks[1] / SW2_CT) * g.K[0] + ks[0];
+    outi[6] = ks[0];
+    outi[7] = cbin[key + 1] - (int)i;
+    double sn, cs;
+    sincos(ph, &sn, &cs);
+    out[16] = (float)cs;
+    out[17] = (float)sn;
+    outi[18] = m;
+}
+
 __global__ void k_bin_start(const int* __restrict__ sorted_keys, long long M, int nbins,
                              int* __restrict__ bin_start) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,6 +604,75 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     } else {
         p->has_col = false;
     }
+    // ---- 2-D multi-coil row sweep: sort by (strip, first row), records, work items, modulation tables ----
+    p->has_sw2 = sweep2d_supported(g) && M > 0;
+    if (p->has_sw2) {
+        const int nq = (g.K[1] + SW2_CT - 1) / SW2_CT;
+        const int n_sbins = nq * g.K[0];
+        PLAN_TRY(cudaMalloc(&p->d_sw_perm, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&p->d_sw_rec, sizeof(float) * M * SW2_RECW));
+        p->bytes += sizeof(int) * M + sizeof(float) * M * SW2_RECW;
+        {   // modulation tables m_d[g] = exp(i s_d g), concatenated [K0 | K1]
+            std::vector<float2> hm(g.K[0] + g.K[1]);
+            int o = 0;
+            for (int d = 0; d < 2; ++d) {
+                const double sd = pc.gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+                for (int t = 0; t < g.K[d]; ++t) hm[o + t] = make_float2((float)cos(sd * t), (float)sin(sd * t));
+                o += g.K[d];
+            }
+            PLAN_TRY(cudaMalloc(&p->d_mod, sizeof(float2) * hm.size()));
+            PLAN_TRY(cudaMemcpyAsync(p->d_mod, hm.data(), sizeof(float2) * hm.size(), cudaMemcpyHostToDevice, st));
+            PLAN_TRY(cudaStreamSynchronize(st));
+        }
+        DevTmp t_keys, t_keys_s, t_vals, t_cbin, t_tmp;
+        PLAN_TRY(cudaMalloc(&t_keys.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_keys_s.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_vals.p, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&t_cbin.p, sizeof(int) * (n_sbins + 1)));
+        int *d_keys = t_keys.as<int>(), *d_keys_s = t_keys_s.as<int>(), *d_vals = t_vals.as<int>(), *d_cbin = t_cbin.as<int>();
+        const int TB = 256;
+        const unsigned nblk = (unsigned)((M + TB - 1) / TB);
+        k_sw2_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, d_keys, d_vals);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        int end_bit = 1;
+        while ((1LL << end_bit) < n_sbins) ++end_bit;
+        size_t tmp_bytes = 0;
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_sw_perm, (int)M, 0,
+                                                 end_bit, st));
+        PLAN_TRY(cudaMalloc(&t_tmp.p, tmp_bytes));
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(t_tmp.p, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_sw_perm, (int)M, 0,
+                                                 end_bit, st));
+        k_bin_start<<<(n_sbins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, n_sbins, d_cbin);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        k_sw2_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_sw_perm, M, d_cbin, p->d_sw_rec);
+        g_launches++;
+        PLAN_TRY(cudaGetLastError());
+        std::vector<int> h_cbin(n_sbins + 1, 0);
+        PLAN_TRY(cudaMemcpyAsync(h_cbin.data(), d_cbin, sizeof(int) * (n_sbins + 1), cudaMemcpyDeviceToHost, st));
+        PLAN_TRY(cudaStreamSynchronize(st));
+        // every strip's samples (already in row order) are cut into segments of at most SW2_SEG samples, heaviest
+        // strips first (radial trajectories are dense at the centre of k-space)
+        std::vector<WorkItem> sw;
+        int seg = SW2_SEG;
+        if (const char* e = getenv("B200NUFFT_SW2_SEG")) seg = std::max(16, atoi(e));    // tuning knob
+        for (int q = 0; q < nq; ++q) {
+            const int b = h_cbin[(size_t)q * g.K[0]], e = h_cbin[(size_t)(q + 1) * g.K[0]];
+            const int n = e - b;
+            if (n <= 0) continue;
+            const int nseg = (n + seg - 1) / seg;
+            for (int sgi = 0; sgi < nseg; ++sgi) {
+                const int sb = b + (int)((long long)n * sgi / nseg), se = b + (int)((long long)n * (sgi + 1) / nseg);
+                if (se > sb) sw.push_back(WorkItem{q, sb, se, 0});
+            }
+        }
+        p->n_sw_work = (int)sw.size();
+        PLAN_TRY(cudaMalloc(&p->d_sw_work, sizeof(WorkItem) * sw.size()));
+        PLAN_TRY(cudaMemcpyAsync(p->d_sw_work, sw.data(), sizeof(WorkItem) * sw.size(), cudaMemcpyHostToDevice, st));
+        PLAN_TRY(cudaStreamSynchronize(st));
+        p->bytes += sizeof(WorkItem) * sw.size();
+    }
 #undef PLAN_TRY
     *out = p;
     return B200_OK;
@@ -571,6 +696,9 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_crec);
     cudaFree(p->d_cside);
     cudaFree(p->d_cwork);
+    cudaFree(p->d_sw_perm);
+    cudaFree(p->d_sw_rec);
+    cudaFree(p->d_sw_work);
     cudaFree(p->d_mod);
     cudaFree(p->d_ccount);
     cudaFree(p->d_ys);
@@ -579,15 +707,20 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_tw256);
     cudaFree(p->d_xc);
     cudaFree(p->d_grid);
+    cudaFree(p->d_grid2);
     cudaFree(p->d_xin);
     cudaFree(p->d_yio);
     if (p->fft_valid) cufftDestroy(p->fft);
     if (p->fftp_valid) { cufftDestroy(p->fft2d); cufftDestroy(p->fft1d); }
+    if (p->fft_bi_valid) cufftDestroy(p->fft_bi);
     delete p;
     return B200_OK;
 }
 
-extern "C" int b200nufft_plan_get_layout(b200nufft_plan_t p) { return p ? (p->has_col ? 1 : 0) : -1; }
+extern "C" int b200nufft_plan_get_layout(b200nufft_plan_t p) { return p ? ((p->has_col || p->has_sw2) ? 1 : 0) : -1; }
+// 1 if grids handed to / returned by the stage entry points for a call with nb coils are BATCH-INNERMOST
+// (k[K0][K1][nb], the reference's Kd + (batch,) order), 0 if they are coil-major (nb contiguous Kd grids)
+extern "C" int b200nufft_grid_layout(b200nufft_plan_t p, int nb) { return (p && use_bi(p, nb)) ? 1 : 0; }
 
 static int run_export(b200nufft_plan_t p, uint32_t* kindx, float2* udata, int* k0, void* stream) {
     ARG_CHECK(p != nullptr, "plan is NULL");
@@ -627,7 +760,16 @@ extern "C" int b200nufft_plan_get_tile(b200nufft_plan_t p, int32_t* tile_host) {
 // key = (q1 * nq2 + q2) * K0 + first plane, i.e. the generic bin key with tile = (K0, T1, T2), sub-tile = (1, T1, T2)
 extern "C" int b200nufft_plan_get_col_perm(b200nufft_plan_t p, int32_t* perm, int32_t* tile_host, void* stream) {
     ARG_CHECK(p != nullptr, "plan is NULL");
-    ARG_CHECK(p->has_col, "plan has no column-sweep records");
+    ARG_CHECK(p->has_col || p->has_sw2, "plan has no sweep records");
+    if (p->has_sw2) {               // 2-D: tile = (K0, 3), sub-tile = (1, 3) in the first four entries
+        if (tile_host) {
+            const int t[6] = {p->g.K[0], SW2_CT, 1, SW2_CT, 0, 0};
+            for (int i = 0; i < 6; ++i) tile_host[i] = t[i];
+        }
+        if (perm && p->M > 0)
+            CUDA_TRY(cudaMemcpyAsync(perm, p->d_sw_perm, sizeof(int) * p->M, cudaMemcpyDeviceToDevice, as_stream(stream)));
+        return B200_OK;
+    }
     if (tile_host) {
         const int t[6] = {p->g.K[0], COL_T1, COL_T2, 1, COL_T1, COL_T2};
         for (int i = 0; i < 6; ++i) tile_host[i] = t[i];

@@ -166,6 +166,9 @@ extern "C" int b200nufft_scale_pad(b200nufft_plan_t p, const b200_c64* x, b200_c
                                    int apply_sn, int x_single, const b200_c64* sens, void* stream) {
     ARG_CHECK(p && x && grid && nb >= 1 && nb <= 65535, "scale_pad: bad arguments");
     ON_DEVICE(p->device);
+    if (use_bi(p, nb))
+        return sweep2d_scale_pad(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
+                                 x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
     const Geom& g = p->g;
     const int dl = g.ndim - 1;
     const int nrows = (int)(g.Kprod / g.K[dl]);
@@ -242,6 +245,14 @@ static int fft_pruned(b200nufft_plan_t p, float2* grid, int nb, int mode, cudaSt
 extern "C" int b200nufft_fft(b200nufft_plan_t p, b200_c64* grid, int nb, int inverse, void* stream) {
     ARG_CHECK(p && grid && nb >= 1 && inverse >= 0 && inverse <= 4, "fft: bad arguments");
     ON_DEVICE(p->device);
+    if (use_bi(p, nb)) {
+        int rc = sweep2d_fft(p, reinterpret_cast<float2*>(grid), nb, (inverse == 0 || inverse == 3) ? 0 : 1, as_stream(stream));
+        if (rc || inverse != 1) return rc;
+        k_scale_inplace<<<148 * 8, 256, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(grid), p->g.Kprod * nb,
+                                                               1.0f / (float)p->g.Kprod);
+        LAUNCH_CHECK();
+        return B200_OK;
+    }
     if (inverse >= 3) {
         if (can_prune(p->g)) return fft_pruned(p, reinterpret_cast<float2*>(grid), nb, inverse, as_stream(stream));
         inverse = inverse == 3 ? 0 : 2;
@@ -262,7 +273,8 @@ extern "C" int b200nufft_fft(b200nufft_plan_t p, b200_c64* grid, int nb, int inv
 }
 
 static int crop_scale_impl(b200nufft_plan_t p, const float2* grid, float2* x, int nb, int mode, int combine,
-                           const float2* sens, float scale, cudaStream_t st) {
+                           const float2* sens, float scale, cudaStream_t st, bool coil_major = false) {
+    if (!coil_major && use_bi(p, nb)) return sweep2d_crop_scale(p, grid, x, nb, mode, combine, sens, scale, st);
     const int TB = 256;
     if (combine) {
         k_crop_combine<<<(unsigned)((p->g.Nprod + TB - 1) / TB), TB, 0, st>>>(p->g, p->d_sn, grid, x, nb, mode,
@@ -291,6 +303,14 @@ int ensure_scratch(b200nufft_plan_t p, int nb) {
     return B200_OK;
 }
 
+int ensure_scratch2(b200nufft_plan_t p, int nb) {
+    if (p->grid2_nb >= nb) return B200_OK;
+    if (p->d_grid2) { CUDA_TRY(cudaFree(p->d_grid2)); p->d_grid2 = nullptr; p->grid2_nb = 0; }
+    CUDA_TRY(cudaMalloc(&p->d_grid2, sizeof(float2) * p->g.Kprod * nb));
+    p->grid2_nb = nb;
+    return B200_OK;
+}
+
 // pad_fft: grid = FFT(zero-pad(x * [sn] * [sens])).  Fused pruned passes when the geometry allows
 // (fft256.cu), else scale_pad + cuFFT (pruned plan for other 3-D sizes).
 // `modulated`: leave the grid phase-modulated, G'[g] = G[g] prod_d m_d[g_d] (what the column-sweep gather reads)
@@ -305,6 +325,9 @@ static int pad_fft_impl(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, i
     if (p->fft_variant != 1 && fft256_supported(p->g))
         return fft256_forward(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
                               x_single, reinterpret_cast<const float2*>(sens), modulated, as_stream(stream));
+    if (use_bi(p, nb))              // batch-innermost grid out: coil-major pad + cuFFT on a scratch, one transposing pass
+        return sweep2d_pad_fft(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
+                               x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
     int rc = b200nufft_scale_pad(p, x, grid, nb, apply_sn, x_single, sens, stream);
     if (rc) return rc;
     rc = b200nufft_fft(p, grid, nb, 3, stream);
@@ -348,6 +371,12 @@ static int ifft_crop_impl(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int n
                              p->g.Nprod, nb, st);
     }
     int rc = B200_OK;
+    if (use_bi(p, nb)) {            // batch-innermost grid in: one transposing pass, cuFFT and crop on the coil-major scratch
+        rc = sweep2d_ifft_to_scratch(p, reinterpret_cast<const float2*>(grid), nb, st);
+        if (rc) return rc;
+        return crop_scale_impl(p, p->d_grid2, reinterpret_cast<float2*>(x), nb, mode, combine,
+                               reinterpret_cast<const float2*>(sens), scale, st, true);
+    }
     if (mod) {
         rc = col3d_demodulate(p, reinterpret_cast<float2*>(grid), nb, st);
         if (rc) return rc;

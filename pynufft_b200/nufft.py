@@ -188,15 +188,23 @@ class NUFFT:
             raise ValueError('%s has shape %s, expected %s(+batch)' % (what, tuple(t.shape), tuple(shape_prefix)))
         return t.contiguous()
 
+    def _bi(self, nb):
+        """True when the library takes the grids of an nb-coil call batch-innermost (Kd + (nb,) contiguous, the
+        reference's own layout; 2-D multi-coil kernels, csrc/sweep2d.cu) instead of coil-major ((nb,) + Kd)."""
+        return int(self._lib.b200nufft_grid_layout(self._plan, int(nb))) == 1
+
     def _new_grid(self, nb, batched):
-        """(Kd(+ (B,)) view, contiguous coil-major storage (B, *Kd)) of a fresh grid."""
+        """(Kd(+ (B,)) view, contiguous storage in the library's layout) of a fresh grid."""
+        if batched and self._bi(nb):
+            store = torch.empty(tuple(self.Kd) + (nb,), dtype=torch.complex64, device=self.device)
+            return store, store
         store = torch.empty((nb,) + tuple(self.Kd), dtype=torch.complex64, device=self.device)
         if not batched:
             return store[0], store
         return store.permute(*range(1, self.ndims + 1), 0), store
 
     def _grid_storage(self, k, what='k'):
-        """Return (coil-major contiguous storage tensor, nb, batched) for a user grid tensor."""
+        """Return (contiguous storage tensor in the library's layout, nb, batched) for a user grid tensor."""
         if not (isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.complex64):
             raise TypeError('%s must be a CUDA complex64 torch tensor' % what)
         if tuple(k.shape[:self.ndims]) != tuple(self.Kd):
@@ -204,12 +212,14 @@ class NUFFT:
         nb = self._nb_of(k, self.ndims, what)
         if k.dim() == self.ndims:
             return k.contiguous(), 1, False
+        if self._bi(nb):
+            return k.contiguous(), nb, True      # batch-innermost: the user's Kd + (B,) array as it is
         cm = k.permute(self.ndims, *range(self.ndims))
         return cm.contiguous(), nb, True         # no copy when k is already a coil-major view
 
     def _view_of(self, store, nb, batched):
-        """Kd(+B) view of a coil-major storage tensor produced by _new_grid / _grid_storage."""
-        if not batched:
+        """Kd(+B) view of a storage tensor produced by _new_grid / _grid_storage."""
+        if not batched or self._bi(nb):
             return store
         return store.permute(*range(1, self.ndims + 1), 0)
 
@@ -485,10 +495,11 @@ class NUFFT:
         perm = torch.empty((self.M,), dtype=torch.int32, device=self.device)
         tile = numpy.zeros(6, dtype=numpy.int32)
         _lib.check(self._lib.b200nufft_plan_get_col_perm(self._plan, _ptr(perm), tile.ctypes.data, self._stream()))
-        return perm.cpu().numpy(), tuple(int(v) for v in tile[:3]), tuple(int(v) for v in tile[3:])
+        nd = self.ndims
+        return perm.cpu().numpy(), tuple(int(v) for v in tile[:nd]), tuple(int(v) for v in tile[nd:2 * nd])
 
     def layout(self):
-        """1 if the plan also holds the column-sweep gridding records (3-D, J = 6; csrc/col3d.cu), else 0."""
+        """1 if the plan also holds sweep-ordered records (3-D J = 6: csrc/col3d.cu; 2-D J = 6: csrc/sweep2d.cu), else 0."""
         self._require_plan()
         return int(self._lib.b200nufft_plan_get_layout(self._plan))
 

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libb200nufft.so')
-SOURCES = ['plan.cu', 'stages.cu', 'interp_generic.cu', 'col3d.cu', 'interp_tiled.cu', 'grid_tiled.cu', 'fft256.cu', 'sweep2d.cu', 'single2d.cu', 'solver.cu']
+SOURCES = ['plan.cu', 'stages.cu', 'interp_generic.cu', 'col3d.cu', 'interp_tiled.cu', 'grid_tiled.cu', 'fft256.cu', 'sweep2d.cu', 'fftbi.cu', 'single2d.cu', 'solver.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
 # tuning experiments: extra -D definitions (part of the source hash, so a change rebuilds the library)

@@ -173,6 +173,8 @@ struct b200nufft_plan_s {
     int fft_bi_nb = 0;
     bool fft_bi_valid = false;
     bool attr_sw2 = false;
+    float2* d_fbi_tw = nullptr;     // fftbi.cu: twiddle tables [K0 | K1]
+    int* d_fbi_rev = nullptr;       // fftbi.cu: digit-reversal tables [K0 | K1]
     int* d_ccount = nullptr;        // per-coil work counters of the persistent column kernels
     int ccount_nb = 0;
     int n_sm = 0;
@@ -280,6 +282,11 @@ int sweep2d_crop_scale(b200nufft_plan_t p, const float2* grid_bi, float2* x, int
 int sweep2d_fft(b200nufft_plan_t p, float2* grid_bi, int nb, int inverse, cudaStream_t st);
 int sweep2d_pad_fft(b200nufft_plan_t p, const float2* x, float2* grid_bi, int nb, int apply_sn, int x_single,
                     const float2* sens, cudaStream_t st);
+// fftbi.cu: fused, pruned FFT passes on batch-innermost grids (power-of-two Kd, 64 .. 1024)
+bool fftbi_supported(const Geom& g);
+int fftbi_forward(b200nufft_plan_t p, const float2* x, float2* grid_bi, int nb, int apply_sn, int x_single,
+                  const float2* sens, cudaStream_t st);
+int fftbi_inverse(b200nufft_plan_t p, float2* grid_bi, float2* x, int nb, int mode, float scale, cudaStream_t st);
 int sweep2d_ifft_to_scratch(b200nufft_plan_t p, const float2* grid_bi, int nb, cudaStream_t st);   // coil-major result in p->d_grid2
 
 

@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(TPB) k_fft256(PassArgs a, const float2* __rest
     }
 }
 
-__global__ void k_combine_coils(const float2* __restrict__ xc, const float2* __restrict__ sens,
-                                float2* __restrict__ s, long long N, int nb) {
+__global__ void k_combine_coils_few(const float2* __restrict__ xc, const float2* __restrict__ sens,
+                                    float2* __restrict__ s, long long N, int nb) {
     const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n >= N) return;
     float2 acc = make_float2(0.f, 0.f);
@@ -220,6 +220,30 @@ __global__ void k_combine_coils(const float2* __restrict__ xc, const float2* __r
     }
     const float f = 1.0f / (float)nb;
     s[n] = make_float2(acc.x * f, acc.y * f);
+}
+
+// one warp per pixel, lanes over the coils (contiguous in the image layout): s[n] = (1/nb) sum_c conj(sens[n,c]) xc[n,c]
+__global__ void k_combine_coils(const float2* __restrict__ xc, const float2* __restrict__ sens,
+                                float2* __restrict__ s, long long N, int nb) {
+    const int lane = threadIdx.x & 31;
+    const long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int c = lane; c < nb; c += 32) {
+        float2 v = xc[n * nb + c];
+        if (sens) v = cmulc(sens[n * nb + c], v);
+        acc.x += v.x;
+        acc.y += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (lane == 0) {
+        const float f = 1.0f / (float)nb;
+        s[n] = make_float2(acc.x * f, acc.y * f);
+    }
 }
 
 }  // namespace
@@ -306,7 +330,11 @@ int fft256_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode
 
 int combine_coils(const float2* xc, const float2* sens, float2* s, long long N, int nb, cudaStream_t st) {
     const int TB = 256;
-    k_combine_coils<<<(unsigned)((N + TB - 1) / TB), TB, 0, st>>>(xc, sens, s, N, nb);
+    if (nb < 8) {       // few coils: one thread per pixel
+        k_combine_coils_few<<<(unsigned)((N + TB - 1) / TB), TB, 0, st>>>(xc, sens, s, N, nb);
+    } else {
+        k_combine_coils<<<(unsigned)((N * 32 + TB - 1) / TB), TB, 0, st>>>(xc, sens, s, N, nb);
+    }
     LAUNCH_CHECK();
     return B200_OK;
 }

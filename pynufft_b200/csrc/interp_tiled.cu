@@ -34,7 +34,13 @@ constexpr int NPL = TS + TJ - 1;          // 13 planes
 constexpr int RP = 21;                    // row pitch (complex), odd
 constexpr int PP = 446;                   // plane pitch (complex) >= 21*21, == 6*RP (mod 16)
 constexpr int TILE_ELEMS = NPL * PP;      // 5798
-constexpr int SUBCHUNK = 256;             // samples per record sub-chunk
+#ifndef IT_SUBCHUNK
+#define IT_SUBCHUNK 256
+#endif
+#ifndef IT_CTAS
+#define IT_CTAS 3
+#endif
+constexpr int SUBCHUNK = IT_SUBCHUNK;     // samples per record sub-chunk
 constexpr int SRW = 24;                   // words per record
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
@@ -99,7 +105,7 @@ __device__ __forceinline__ int wrap2s(int i, int K, float sg, float& sign) {   /
 }
 
 template <bool MOD>
-__global__ void __launch_bounds__(NTHREADS, 3)
+__global__ void __launch_bounds__(NTHREADS, IT_CTAS)
 k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restrict__ rec,
                const float2* __restrict__ grid, float2* __restrict__ y, int nb, const float2* __restrict__ mod) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

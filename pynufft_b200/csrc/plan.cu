@@ -708,6 +708,8 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_xc);
     cudaFree(p->d_grid);
     cudaFree(p->d_grid2);
+    cudaFree(p->d_fbi_tw);
+    cudaFree(p->d_fbi_rev);
     cudaFree(p->d_xin);
     cudaFree(p->d_yio);
     if (p->fft_valid) cufftDestroy(p->fft);

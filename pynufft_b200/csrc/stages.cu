@@ -325,6 +325,9 @@ static int pad_fft_impl(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, i
     if (p->fft_variant != 1 && fft256_supported(p->g))
         return fft256_forward(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
                               x_single, reinterpret_cast<const float2*>(sens), modulated, as_stream(stream));
+    if (use_bi(p, nb) && p->fft_variant != 1 && fftbi_supported(p->g))     // fused pruned passes on the layout itself
+        return fftbi_forward(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
+                             x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
     if (use_bi(p, nb))              // batch-innermost grid out: coil-major pad + cuFFT on a scratch, one transposing pass
         return sweep2d_pad_fft(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
                                x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
@@ -371,6 +374,19 @@ static int ifft_crop_impl(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int n
                              p->g.Nprod, nb, st);
     }
     int rc = B200_OK;
+    if (use_bi(p, nb) && p->fft_variant != 1 && fftbi_supported(p->g)) {
+        if (!combine)
+            return fftbi_inverse(p, reinterpret_cast<float2*>(grid), reinterpret_cast<float2*>(x), nb, mode, scale, st);
+        if (p->xc_nb < nb) {
+            if (p->d_xc) { CUDA_TRY(cudaFree(p->d_xc)); p->d_xc = nullptr; p->xc_nb = 0; }
+            CUDA_TRY(cudaMalloc(&p->d_xc, sizeof(float2) * p->g.Nprod * nb));
+            p->xc_nb = nb;
+        }
+        rc = fftbi_inverse(p, reinterpret_cast<float2*>(grid), p->d_xc, nb, mode, scale, st);
+        if (rc) return rc;
+        return combine_coils(p->d_xc, reinterpret_cast<const float2*>(sens), reinterpret_cast<float2*>(x), p->g.Nprod, nb,
+                             st);
+    }
     if (use_bi(p, nb)) {            // batch-innermost grid in: one transposing pass, cuFFT and crop on the coil-major scratch
         rc = sweep2d_ifft_to_scratch(p, reinterpret_cast<const float2*>(grid), nb, st);
         if (rc) return rc;

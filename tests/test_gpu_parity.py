@@ -14,7 +14,6 @@ from oracle import nufft_oracle as orc
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-CG10_BOUND, CG100_BOUND = 1.0, 1.0      # placeholders until measured
 
 
 def rel(a, b):
@@ -534,7 +533,10 @@ def test_config4_solvers(c2, dev):
     # solver and the numpy restatement of the device arithmetic (orc.solve_cg, pinned to the reference's own
     # solve_device.py by the cg10 goldens) round at the same places and follow the same perturbed trajectory.  Parity is
     # agreement with that restatement; both runs are stored by oracle/make_cg_fixture.py at 60 000 entries of the result
-    # (tests/golden/c4_cg_c128.npz; the 100-iteration CPU runs take minutes).  Bounds: 4x what B200 measured (printed).
+    # (tests/golden/c4_cg_c128.npz; the 100-iteration CPU runs take minutes).  Measured on B200: after 10 iterations the
+    # CUDA solver is 3.5e-4 from the restatement (norm 1.1e-5); after 100 iterations it is 3.1e-3 from the EXACT iterates,
+    # closer than the restatement itself (1.5e-2: the CUDA solver keeps the CG scalars in float64), so the 100-iteration
+    # bound is taken against the exact iterates.  Bounds are 4x the measured values.
     import os
     from conftest import GOLDEN
     fx = dict(numpy.load(os.path.join(GOLDEN, 'c4_cg_c128.npz')))
@@ -549,9 +551,10 @@ def test_config4_solvers(c2, dev):
     print('config-4 CG vs complex64 restatement: 10 it %.3e (norm %.1e), 100 it %.3e (norm %.1e); vs exact iterates: '
           '%.3e, %.3e (restatement vs exact: %.3e, %.3e)' % (e10, n10, e100, n100, x10e, x100e,
                                                              rel(fx['x10_c64'], fx['x10']), rel(fx['x100_c64'], fx['x100'])))
-    assert e10 < CG10_BOUND and n10 < CG10_BOUND, (e10, n10)
-    assert e100 < CG100_BOUND and n100 < CG100_BOUND, (e100, n100)
-    assert x100e < 2 * rel(fx['x100_c64'], fx['x100'])      # no further from exact arithmetic than the restatement is
+    assert e10 < 1.5e-3 and n10 < 1e-4, (e10, n10)
+    assert x100e < 1.3e-2, x100e
+    assert x100e < rel(fx['x100_c64'], fx['x100'])          # no further from exact arithmetic than the restatement is
+    assert e100 < 2 * rel(fx['x100_c64'], fx['x100']) and n100 < 1e-2, (e100, n100)
     # multi-coil L1TVOLS (TV-SENSE closures: AH = adjoint_many2one, AHA = selfadjoint_one2many2one,
     # linalg/solve_hsa.py:275-476 with :282-287 on the batch operator) at configuration-4 size
     xl = A.solve(y, 'L1TVOLS', maxiter=5, rho=2)

@@ -130,6 +130,9 @@ constexpr int COL_T1 = 4, COL_T2 = 5, COL_RECW = 32, COL_SEG = 320;
 // 2-D multi-coil row sweep (sweep2d.cu): strips of SW2_CT first-neighbour columns (dim 1) swept along dim 0, coil on the
 // lanes; 20-word sample records in sweep order
 constexpr int SW2_CT = 3, SW2_RECW = 20, SW2_SEG = 64;
+// tiled 3-D gather (interp_tiled.cu): row / plane pitch (complex elements) of the staged 13 x 21 x 21 box; the plan bakes the
+// box-relative address of a sample's first neighbour into its gather record
+constexpr int TILE_RP = 21, TILE_PP = 446, TILE_RECW = 24;
 
 struct WorkItem {   // one launch unit of the tiled kernels: samples [begin, end) of one tile
     int tile;
@@ -148,6 +151,7 @@ struct b200nufft_plan_s {
     double* d_om = nullptr;         // (M, ndim) original order
     int* d_perm = nullptr;          // (M,)
     float* d_rec = nullptr;         // (M, recw) sorted order
+    float* d_trec = nullptr;        // (M, TILE_RECW) sorted order: records of the tiled 3-D gather, ready to use
     float* d_sn = nullptr;          // (sum N)
     int* d_bin_start = nullptr;     // (n_bins + 1), n_bins = n_tiles * nsubprod
     WorkItem* d_work = nullptr;     // interp: per tile

@@ -31,8 +31,8 @@ constexpr int TT = 16;                    // tile edge (dims 1, 2)
 constexpr int TS = 8;                     // slab thickness (dim 0)
 constexpr int BOX = TT + TJ - 1;          // 21
 constexpr int NPL = TS + TJ - 1;          // 13 planes
-constexpr int RP = 21;                    // row pitch (complex), odd
-constexpr int PP = 446;                   // plane pitch (complex) >= 21*21, == 6*RP (mod 16)
+constexpr int RP = TILE_RP;               // row pitch (complex), odd: 21
+constexpr int PP = TILE_PP;               // plane pitch (complex) >= 21*21, == 6*RP (mod 16): 446
 constexpr int TILE_ELEMS = NPL * PP;      // 5798
 #ifndef IT_SUBCHUNK
 #define IT_SUBCHUNK 256
@@ -44,11 +44,11 @@ constexpr int SUBCHUNK = IT_SUBCHUNK;     // samples per record sub-chunk
 constexpr int SRW = 24;                   // words per record
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int RECW = 24;                  // words per plan record (3 x 6 + 2 + 3 + 1)
+constexpr int RECW = TILE_RECW;           // words per gather record (plan.cu k_build_records): 24
 constexpr size_t SMEM_BYTES = TILE_ELEMS * sizeof(float2) + SUBCHUNK * SRW * sizeof(float) + 16;
 
-// record after fix-up: [c0[6] | c1[6] | c2[6] | base, perm | P'.re, P'.im | (ks2, perm)]
-//                       0       6       12      18    19     20     21
+// gather record: [c0[6] | c1[6] | c2[6] | base, perm | P'.re, P'.im | P''.re, P''.im]   (built at plan time)
+//                 0       6       12      18    19     20     21      22      23
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -207,33 +207,10 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
         }
         mbar_wait(mbar, phase);
         phase ^= 1;
-        // ---- in-place fix-up: [.. | P.re P.im | ks0 ks1 ks2 perm] -> [.. | base perm | P'.re P'.im | ..] ----
-        if (tid < nsr) {
-            float* R = srec + tid * SRW;
-            if (tid < ns) {
-                const float2 Pr = *reinterpret_cast<const float2*>(R + 18);
-                const float4 v5 = *reinterpret_cast<const float4*>(R + 20);
-                const int ks0 = __float_as_int(v5.x), ks1 = __float_as_int(v5.y), ks2 = __float_as_int(v5.z);
-                const int base = (ks0 - T0) * PP + (ks1 - T1) * RP + (ks2 - T2);
-                float2 Pp;
-                if (MOD) {          // P * prod_d e^{i s_d} conj(m_d[k_d]),  m_d[k] = e^{i s_d k}
-                    const float2 e = cmul(cmul(g.E[0][0], g.E[1][0]), g.E[2][0]);
-                    const float2 m = cmul(cmul(__ldg(mod + ks0), __ldg(mod + g.K[0] + ks1)), __ldg(mod + g.K[0] + g.K[1] + ks2));
-                    Pp = cmul(Pr, cmulc(m, e));
-                } else {
-                    Pp = cmul(Pr, g.Gl[ks2 - T2]);
-                }
-                *reinterpret_cast<float2*>(R + 18) = make_float2(__int_as_float(base), v5.w);
-                *reinterpret_cast<float2*>(R + 20) = Pp;
-            } else {
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4* R4 = reinterpret_cast<float4*>(R);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) R4[q] = z;
-                R[19] = __int_as_float(-1);
-            }
-        }
-        __syncthreads();    // tile staged + records fixed up
+        // the rows that pad the chunk to a multiple of 8 samples hold stale (first chunk: uninitialised) words: give them a
+        // valid box address; their results are never stored
+        if (tid < nsr - ns) srec[(ns + tid) * SRW + 18] = 0.f;
+        __syncthreads();    // tile staged, chunk complete
 
         // ---- main loop: 8 samples per warp pass ----
         for (int b = warp; b < (nsr >> 3); b += NWARPS) {
@@ -301,7 +278,7 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
                 if (s < ns) {
                     const float* R = srec + s * SRW;
                     const int m = __float_as_int(R[19]);
-                    y[(long long)m * nb + c] = cmul(make_float2(R[20], R[21]), acc[0]);
+                    y[(long long)m * nb + c] = cmul(MOD ? make_float2(R[22], R[23]) : make_float2(R[20], R[21]), acc[0]);
                 }
             }
         }
@@ -312,7 +289,7 @@ k_interp_tiled(Geom g, const WorkItem* __restrict__ work, const float* __restric
 }  // namespace
 
 bool tiled_supported(const Geom& g) {
-    if (g.ndim != 3 || g.recw != RECW) return false;
+    if (g.ndim != 3) return false;
     for (int d = 0; d < 3; ++d)
         if (g.J[d] != TJ || g.tile[d] != TT || g.sub[d] != TS) return false;
     return true;
@@ -331,9 +308,9 @@ int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int n
     if (p->n_work == 0) return B200_OK;
     dim3 gr(p->n_work, nb);
     if (modulated)
-        k_interp_tiled<true><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_rec, grid, y, nb, p->d_mod);
+        k_interp_tiled<true><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_trec, grid, y, nb, p->d_mod);
     else
-        k_interp_tiled<false><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_rec, grid, y, nb, nullptr);
+        k_interp_tiled<false><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_trec, grid, y, nb, nullptr);
     LAUNCH_CHECK();
     return B200_OK;
 }

@@ -104,19 +104,34 @@ __global__ void k_bin_keys(Geom g, const PlanConst* __restrict__ pc, const doubl
 
 // one thread per sorted sample: gather om through perm, write the record
 // record words: [c_0[0..J0) | c_1 | c_2 | P.re P.im | kstart_0.. | perm | pad]
+// trec (3-D tiled gather, may be NULL): [c_0[6] c_1[6] c_2[6] | base perm | P'.re P'.im | P''.re P''.im], where
+//   base = rel0 * TILE_PP + rel1 * TILE_RP + rel2, rel = first neighbour relative to its 8 x 16 x 16 slab,
+//   P'  = P * exp(-i s_2 rel2)                       (true grid: the staged box carries exp(+i s_2 (column + 1)))
+//   P'' = prod_d exp(i (om N/2 - s dk - s (k0' - 1))) (phase-modulated grid)
 __global__ void k_build_records(Geom g, const PlanConst* __restrict__ pc,
                                 const double* __restrict__ om, const int* __restrict__ perm,
-                                long long M, float* __restrict__ rec) {
+                                long long M, float* __restrict__ rec, float* __restrict__ trec) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= M) return;
     const int m = perm[i];
     float* out = rec + i * g.recw;
     double pr = 1.0, pi = 0.0;
+    double ph1 = 0.0, ph2 = 0.0;
+    int ksv[MAXD] = {0, 0, 0};
     for (int d = 0; d < g.ndim; ++d) {
         DimResult R;
         double o = om[(long long)m * g.ndim + d];
         dim_math(o, d, g, pc, R);
         for (int j = 0; j < g.J[d]; ++j) out[g.Joff[d] + j] = (float)R.c[j];
+        if (trec) {
+            const int k = wrap_index(R.k0 + 1, g.K[d]);
+            ksv[d] = k;
+            const double sd = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
+            const double base_ph = o * (double)g.N[d] / 2.0 - sd * R.dk;
+            ph1 += base_ph - (d == g.ndim - 1 ? sd * (double)(k & 15) : 0.0);
+            ph2 += base_ph - sd * (double)(k - 1);
+            for (int j = 0; j < g.J[d]; ++j) trec[i * TILE_RECW + g.Joff[d] + j] = (float)R.c[j];
+        }
         // P_d = exp(i (om N/2 - gam (N-1)/2 dk))
         double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
         double ph = o * (double)g.N[d] / 2.0 - s * R.dk;
@@ -132,6 +147,18 @@ __global__ void k_build_records(Geom g, const PlanConst* __restrict__ pc,
     out[g.sumJ + 1] = (float)pi;
     reinterpret_cast<int*>(out)[g.sumJ + 2 + g.ndim] = m;
     for (int w = g.sumJ + 3 + g.ndim; w < g.recw; ++w) out[w] = 0.f;
+    if (trec) {
+        float* t = trec + i * TILE_RECW;
+        reinterpret_cast<int*>(t)[18] = (ksv[0] & 7) * TILE_PP + (ksv[1] & 15) * TILE_RP + (ksv[2] & 15);
+        reinterpret_cast<int*>(t)[19] = m;
+        double sn, cs;
+        sincos(ph1, &sn, &cs);
+        t[20] = (float)cs;
+        t[21] = (float)sn;
+        sincos(ph2, &sn, &cs);
+        t[22] = (float)cs;
+        t[23] = (float)sn;
+    }
 }
 
 // ---- column-sweep gridding (col3d.cu): key = (column, first plane), 32-word records in sweep order ----
@@ -461,7 +488,11 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         k_bin_start<<<(p->n_bins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, p->n_bins, p->d_bin_start);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
-        k_build_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_rec);
+        if (tiled_supported(g)) {
+            PLAN_TRY(cudaMalloc(&p->d_trec, sizeof(float) * Mal * TILE_RECW));
+            p->bytes += sizeof(float) * Mal * TILE_RECW;
+        }
+        k_build_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_perm, M, p->d_rec, p->d_trec);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         PLAN_TRY(cudaMemcpyAsync(h_bin_start.data(), p->d_bin_start, sizeof(int) * (p->n_bins + 1),
@@ -688,6 +719,7 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_om);
     cudaFree(p->d_perm);
     cudaFree(p->d_rec);
+    cudaFree(p->d_trec);
     cudaFree(p->d_sn);
     cudaFree(p->d_bin_start);
     cudaFree(p->d_work);

@@ -383,10 +383,10 @@ k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const f
             ns = 1;
             u = 0;
         } else {
-            // records two chunks ahead, y rows one chunk ahead
+            // records two chunks ahead, y rows one chunk ahead (every lane is done with the buffers they overwrite)
+            __syncwarp();
             if (kc + 2 < nchunks) {
                 fence_proxy_async();
-                __syncwarp();
                 if (lane == 0) issue_rec(kc + 2);
             }
             if (kc + 1 < nchunks) {

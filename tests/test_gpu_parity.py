@@ -406,6 +406,34 @@ def test_multicoil(dev, geom):
     assert rel(A.forward_one2many(s), orc.NUFFT.forward_one2many(_nosense(O), s)) < TOL
 
 
+@pytest.mark.parametrize('geom', [((32, 100), (64, 256), 8), ((500, 20), (1024, 64), 10), ((64, 64), (128, 128), 16)])
+def test_batch_innermost_fft_sizes(dev, geom):
+    """the fused FFT passes on batch-innermost grids (csrc/fftbi.cu): every power-of-two length 64 .. 1024, non-square,
+    pruned (N < K/2 and N close to K), against the oracle; and against the cuFFT detour (variant 1 = generic + cuFFT)"""
+    Nd, Kd, B = geom
+    rng = numpy.random.default_rng(8)
+    om = rng.uniform(-numpy.pi, numpy.pi, (3000, 2))
+    sens = coil_maps(Nd, B)
+    s = (rng.standard_normal(Nd) + 1j * rng.standard_normal(Nd)).astype(numpy.complex64)
+    O = orc.NUFFT()
+    O.plan(om, Nd, Kd, (6, 6), batch=B)
+    O.set_sense(sens)
+    A = make(dev, om, Nd, Kd, (6, 6), batch=B)
+    A.set_sense(sens)
+    assert A._bi(B)
+    y = O.forward_one2many(s).astype(numpy.complex64)
+    assert rel(A.forward_one2many(s), y) < TOL
+    assert rel(A.adjoint_many2one(y), O.adjoint_many2one(y)) < TOL
+    xb = (rng.standard_normal(Nd + (B,)) + 1j * rng.standard_normal(Nd + (B,))).astype(numpy.complex64)
+    assert rel(A.xx2k(xb), O.xx2k(xb)) < TOL                       # pad + FFT only (no sn), Kd + (B,) out
+    k = O.xx2k(xb).astype(numpy.complex64)
+    assert rel(A.k2xx(k), O.k2xx(k)) < TOL                         # plain inverse FFT stage (transposing detour) + crop
+    A.set_variant(1, 1)
+    assert not A._bi(B)
+    assert rel(A.forward_one2many(s), y) < TOL
+    A.release()
+
+
 def _nosense(O):
     O.reset_sense()
     return O

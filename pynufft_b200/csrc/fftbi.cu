@@ -14,7 +14,9 @@
 //                 scaled image (cTensorCopy(-1) + cTensorMultiply and the 1/prod(Kd) normalisation)
 // Same arithmetic as the reference's unnormalised forward / normalised inverse DFT (reikna FFT,
 // nufft/_nufft_class_methods_device.py:246-249, 358, 431).
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -283,7 +285,11 @@ static BiPass base_pass(b200nufft_plan_t p, int dim, int nb) {
 template <int DIR>
 static int launch(const BiPass& a, int nlines, int nb, cudaStream_t st) {
     dim3 gr((unsigned)nlines, (unsigned)((nb + NCO - 1) / NCO));
-    const size_t smem = sizeof(float2) * (size_t)a.n * (NCO + 1);
+    size_t smem = sizeof(float2) * (size_t)a.n * (NCO + 1);
+    // tuning knob: resident CTAs per SM (more shared memory per CTA = fewer of them); the number of lines is fixed, so
+    // the best occupancy is the one that makes the number of waves an integer
+    static const int want_ctas = [] { const char* e = getenv("B200NUFFT_FBI_CTAS"); return e ? atoi(e) : 0; }();
+    if (want_ctas > 0) smem = std::max(smem, std::min<size_t>((size_t)(227 * 1024) / want_ctas - 1024, sizeof(float2) * 1024 * (NCO + 1)));
     switch (a.n) {
         case 64: k_fftbi<DIR, 6><<<gr, FTB, smem, st>>>(a); break;
         case 128: k_fftbi<DIR, 7><<<gr, FTB, smem, st>>>(a); break;

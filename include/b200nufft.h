@@ -182,6 +182,11 @@ int b200nufft_cdiv(b200_c64* a, const b200_c64* b, int64_t n, void* stream);
 /* a[i] = a[i] * b[i] (complex) -- `self.W * k` of the Toeplitz-style selfadjoint2,
  * nufft/_nufft_class_methods_cpu.py:216-222 */
 int b200nufft_cmul(b200_c64* a, const b200_c64* b, int64_t n, void* stream);
+/* out = a x + b y, host scalars a, b (complex as two doubles); y NULL or b == 0: out = a x and y is not read.
+ * out may alias x or y.  The vector update of the Krylov family of the CPU solve (linalg/solve_cpu.py:226-288: scipy's
+ * lsqr / lsmr / bicgstab / bicg / gmres / lgmres run these on host arrays; pynufft_b200/krylov.py keeps them on the device). */
+int b200nufft_axpby(b200_c64* out, double a_re, double a_im, const b200_c64* x, double b_re, double b_im,
+                    const b200_c64* y, int64_t n, void* stream);
 /* L1TVOLS, all arrays single-coil images of the plan's Nd (solve_device.py:74-275):
  *   tv_rhs    : rhs = mu*AHyk + lambda * sum_p Dt_p(d_p - b_p)           (:133-154, cDiff :936-950)
  *   tv_shrink : z_p = D_p(x); s_p = z_p + b_p; s = hypot chain + 1e-6; t = shrink(s,1/lambda)/s;

@@ -17,7 +17,7 @@ def __getattr__(name):
     if name == 'NUFFT':
         from .nufft import NUFFT
         return NUFFT
-    if name == 'solve':
-        from . import solve
-        return solve
+    if name in ('solve', 'krylov', 'dist'):
+        import importlib
+        return importlib.import_module('.' + name, __name__)
     raise AttributeError(name)

@@ -9,7 +9,7 @@ LIBPATH = os.path.join(HERE, 'libb200nufft.so')
 MAX_DIM, MAX_J, MAX_L = 3, 16, 32
 
 _c = ctypes
-_vp, _i, _i64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+_vp, _i, _i64, _f, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_double
 
 # name -> (restype, argtypes); mirrors include/b200nufft.h one to one
 SIGNATURES = {
@@ -41,6 +41,7 @@ SIGNATURES = {
     'b200nufft_zero_scalars': (_i, [_vp, _i, _vp]),
     'b200nufft_cg_update_xr': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     'b200nufft_cg_update_p': (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    'b200nufft_axpby': (_i, [_vp, _d, _d, _vp, _d, _d, _vp, _i64, _vp]),
     'b200nufft_cg_init': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     'b200nufft_cdiv': (_i, [_vp, _vp, _i64, _vp]),
     'b200nufft_cmul': (_i, [_vp, _vp, _i64, _vp]),

@@ -129,6 +129,23 @@ __global__ void k_cmul(float2* __restrict__ a, const float2* __restrict__ b, lon
     for (; i < n; i += stride) a[i] = cmul(a[i], b[i]);
 }
 
+// out = a x + b y with host scalars (the vector updates of the Krylov recurrences, pynufft_b200/krylov.py);
+// HAS_Y = false: out = a x and y is never read.  out may alias x or y.
+template <bool HAS_Y>
+__global__ void k_axpby(float2* out, float2 a, const float2* x, float2 b, const float2* y, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float2 r = cmul(a, x[i]);
+        if (HAS_Y) {
+            const float2 t = cmul(b, y[i]);
+            r.x += t.x;
+            r.y += t.y;
+        }
+        out[i] = r;
+    }
+}
+
 // ---- L1TVOLS ---------------------------------------------------------------------------------
 // periodic neighbour along axis d of the linear image index n
 __device__ __forceinline__ long long shifted(const Geom& g, long long n, int d, int step, const int* coord,
@@ -295,6 +312,21 @@ extern "C" int b200nufft_cmul(b200_c64* a, const b200_c64* b, int64_t n, void* s
     ON_DEVICE(device_of(a));
     k_cmul<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(a),
                                                                reinterpret_cast<const float2*>(b), n);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200nufft_axpby(b200_c64* out, double a_re, double a_im, const b200_c64* x, double b_re, double b_im,
+                               const b200_c64* y, int64_t n, void* stream) {
+    ARG_CHECK(out && x && n >= 0, "axpby: bad arguments");
+    ON_DEVICE(device_of(out));
+    const float2 a = make_float2((float)a_re, (float)a_im), b = make_float2((float)b_re, (float)b_im);
+    float2* o = reinterpret_cast<float2*>(out);
+    const float2* xv = reinterpret_cast<const float2*>(x);
+    if (y && (b_re != 0.0 || b_im != 0.0))
+        k_axpby<true><<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(o, a, xv, b, reinterpret_cast<const float2*>(y), n);
+    else
+        k_axpby<false><<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(o, a, xv, b, nullptr, n);
     LAUNCH_CHECK();
     return B200_OK;
 }

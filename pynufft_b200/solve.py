@@ -9,6 +9,7 @@ interp + gridding + 3 fused streaming kernels, and alpha/beta/rho live in a smal
 pynufft_b200/dist.py) the two scalars are summed with one all-reduce each.
 """
 import ctypes
+import math
 
 import numpy
 import torch
@@ -204,32 +205,62 @@ def density_compensation(nufft, gy, maxiter=1):
 KRYLOV = ('lsmr', 'lsqr', 'bicgstab', 'bicg', 'gmres', 'lgmres')
 
 
+class CudaKrylovOps:
+    """The vector interface of pynufft_b200/krylov.py on flat complex64 CUDA tensors: `b200nufft_axpby` for every
+    update, `b200nufft_dotc` (double accumulation, result read back as two doubles) for inner products and norms."""
+
+    def __init__(self, lib, device):
+        self.L = lib
+        self.acc = torch.zeros(2, dtype=torch.float64, device=device)
+
+    def new(self, like):
+        return torch.empty_like(like)
+
+    def dot(self, a, b):
+        self.acc.zero_()
+        _lib.check(self.L.b200nufft_dotc(_ptr(a), _ptr(b), a.numel(), _ptr(self.acc), _stream(a.device)))
+        re, im = self.acc.tolist()
+        return complex(re, im)
+
+    def nrm(self, a):
+        return math.sqrt(max(self.dot(a, a).real, 0.0))
+
+    def axpby(self, out, a, x, b=0.0, y=None):
+        a, b = complex(a), complex(b)
+        _lib.check(self.L.b200nufft_axpby(_ptr(out), a.real, a.imag, _ptr(x), b.real, b.imag,
+                                          _ptr(y) if y is not None else None, out.numel(), _stream(out.device)))
+        return out
+
+
 def krylov(nufft, gy, solver, *args, **kwargs):
-    """The scipy Krylov family of the reference's CPU solve (linalg/solve_cpu.py:226-288) with the
-    device operator as the matvec: 'lsmr' / 'lsqr' on A = k2y (rmatvec y2k), the others on G = y2k . k2y with
-    right-hand side y2k(y); then k2xx and DIVIDE by sn.  scipy runs the recurrences on the host exactly as in the
-    reference (extra positional / keyword arguments go to the scipy routine); every operator application runs on
-    the GPU, its k-space / data vector crossing PCIe once each way.  Single coil."""
-    import scipy.sparse.linalg as sla
+    """The scipy Krylov family of the reference's CPU solve (linalg/solve_cpu.py:226-288): 'lsmr' /
+    'lsqr' on A = k2y (rmatvec y2k), the others on G = y2k . k2y with right-hand side y2k(y); then k2xx and DIVIDE by
+    sn.  The recurrences are scipy's, restated on device vectors (pynufft_b200/krylov.py): the iterates never leave
+    the GPU, only the scalars of the recurrences do.  Extra positional / keyword arguments are the scipy routine's
+    (x0: flat device tensor or array; M: callable on flat device tensors).  Single coil."""
+    from . import krylov as kr
     if nufft.batch not in (None, 1) or gy.dim() != 1:
         raise ValueError('the scipy Krylov solvers are single-coil (as the reference CPU object)')
     Kd, K, M = tuple(nufft.Kd), int(nufft.Kdprod), int(nufft.M)
-    c64 = numpy.complex64
-    dev = lambda a, shape: nufft.to_device(numpy.ascontiguousarray(numpy.asarray(a).reshape(shape), dtype=c64))
-    k2y = lambda k: nufft.to_host(nufft._k2y_device(dev(k, Kd))).ravel()
-    y2k = lambda v: nufft.to_host(nufft._y2k_device(dev(v, (M,)))).ravel()
+    ops = CudaKrylovOps(nufft._lib, nufft.device)
+    flat = lambda view: nufft._grid_storage(view)[0].reshape(-1)
+    k2y = lambda k: nufft._k2y_device(k.view(Kd))
+    y2k = lambda v: flat(nufft._y2k_device(v))
+    if 'x0' in kwargs and kwargs['x0'] is not None and not torch.is_tensor(kwargs['x0']):
+        kwargs['x0'] = nufft.to_device(numpy.ascontiguousarray(numpy.asarray(kwargs['x0']).reshape(Kd),
+                                                               dtype=numpy.complex64)).reshape(-1)
     if solver in ('lsmr', 'lsqr'):
-        A = sla.LinearOperator((M, K), matvec=k2y, rmatvec=y2k, dtype=numpy.complex128)
-        vec = {'lsmr': sla.lsmr, 'lsqr': sla.lsqr}[solver](A, nufft.to_host(gy).ravel(), *args, **kwargs)[0]
+        like = torch.empty(K, dtype=torch.complex64, device=nufft.device)
+        vec = {'lsmr': kr.lsmr, 'lsqr': kr.lsqr}[solver](ops, k2y, y2k, gy.contiguous(), like, *args, **kwargs)[0]
     else:
         G = lambda k: y2k(k2y(k))
-        A = sla.LinearOperator((K, K), matvec=G, rmatvec=G, dtype=numpy.complex128)
-        methods = {'bicgstab': sla.bicgstab, 'bicg': sla.bicg, 'gmres': sla.gmres, 'lgmres': sla.lgmres}
-        vec = methods[solver](A, nufft.to_host(nufft._y2k_device(gy)).ravel(), *args, **kwargs)[0]
-    ks = dev(vec, Kd)
+        b = y2k(gy)
+        if solver == 'bicg':
+            vec = kr.bicg(ops, G, G, b, *args, **kwargs)[0]
+        else:
+            vec = {'bicgstab': kr.bicgstab, 'gmres': kr.gmres, 'lgmres': kr.lgmres}[solver](ops, G, b, *args, **kwargs)[0]
     x2 = torch.empty(tuple(nufft.Nd), dtype=torch.complex64, device=nufft.device)
-    _lib.check(nufft._lib.b200nufft_ifft_crop(nufft._plan, _ptr(nufft._grid_storage(ks)[0]), _ptr(x2), 1, 2, 0, None,
-                                              nufft._stream()))
+    _lib.check(nufft._lib.b200nufft_ifft_crop(nufft._plan, _ptr(vec), _ptr(x2), 1, 2, 0, None, nufft._stream()))
     return x2
 
 

@@ -100,6 +100,12 @@ def test_solvers_match_reference_device_algorithms(golden, dev):
     assert rel(A.solve(y, 'lsqr', iter_lim=6), golden['lsqr6']) < 1e-4
     assert rel(A.solve(y, 'bicgstab', maxiter=3), golden['bicgstab3']) < 1e-4
     assert rel(A.solve(y, 'gmres', maxiter=1, restart=4), golden['gmres1']) < 1e-4
+    # the members without a reference golden: against the oracle's scipy run on the oracle operator
+    O = orc.NUFFT()
+    O.plan(golden['om'], tuple(golden['Nd']), tuple(golden['Kd']), tuple(golden['Jd']))
+    assert rel(A.solve(y, 'bicg', maxiter=3), orc.solve_krylov(O, y, 'bicg', maxiter=3)) < 1e-4
+    assert rel(A.solve(y, 'lgmres', maxiter=2, inner_m=3), orc.solve_krylov(O, y, 'lgmres', maxiter=2, inner_m=3)) < 1e-4
+    assert rel(A.solve(y, 'lsmr', maxiter=4, damp=0.05), orc.solve_krylov(O, y, 'lsmr', maxiter=4, damp=0.05)) < 1e-4
 
 
 # ------------------------------------------------------------------------------ edge cases

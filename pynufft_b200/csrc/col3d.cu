@@ -578,259 +578,6 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// gridding (scatter), ROW-LANE layout: the same sweep with the work of a sample cut from 22 to 16 packed FP32
-// instructions per lane.
-//
-// In k_gridding_col a lane owns 3 box rows x 1 box column x 6 planes and multiplies 18 cells per sample although the
-// sample touches 6 rows x 6 columns of the 9 x 10 box (40 % of the multiplies hit a zero-padded weight).  Here
-//  * a column is a 5 x 8 cross-section (RL_T1 x RL_T2), its box 10 rows x 13 columns (the width only costs registers:
-//    the wider the column, the more samples share one plane flush);
-//  * lane (r, t), r = 0..9, t = 0..2 (30 lanes), owns box row r of the plane slots 2t and 2t + 1 of the 6-slot ring,
-//    all 13 box columns: 26 cells, A[column][slot];
-//  * a sample's 6 columns start at box column coff = 0..7, the same for every lane: the code is unrolled over coff
-//    (one warp-uniform branch per sample) and multiplies only the 6 columns of the footprint.  The plane dimension
-//    needs no unrolling at all: the lane reads the dim-0 weights of ITS two slots from the record, at a lane-dependent
-//    word offset that moves with the window; rows are on the lanes (4 of 10 idle per sample);
-//  * per sample and lane: w = c1[r] * (c0[j(2t)], c0[j(2t+1)]), v = w * y (2 FMUL + 2 FMUL2), then 6 columns x 2 slots
-//    FFMA2 with the warp-uniform column weight as the scalar operand: 16 instead of 22, 60 % useful instead of 40 %;
-//  * the retired plane lives in ONE slot of ONE lane group: its 10 lanes flush 13 columns each with six 16-byte REDs
-//    and one 8-byte RED (rows are 104-byte segments), which needs K2 % 8 == 0 (alignment, and the periodic wrap
-//    falls between box columns 7 and 8).
-// record words: [c2[0..5] | coff - | c1pad[0..9] | p0 run | c0[0..5] | c0[1..5] c0[0]]   (plan.cu k_rl_records)
-//   the second, rotated copy of c0 makes the pair (c0[j], c0[j+1 mod 6]) an aligned 8-byte load for odd j too.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int RT1 = RL_T1, RT2 = RL_T2;   // 5 x 8 columns
-constexpr int RROWS = RT1 + 5;            // 10 box rows = lanes of a plane group
-constexpr int RCOLS = RT2 + 5;            // 13 box columns = registers
-static_assert(RT1 == 5 && RT2 == 8 && 3 * RROWS <= 32, "lane layout below");
-#ifndef RL_CTAS
-#define RL_CTAS 4
-#endif
-
-// a = 0 where pred != 0, as predicated moves: a divergent `if` around the clears makes the compiler shuttle every
-// accumulator through a second register set at each plane
-__device__ __forceinline__ void zero_if(float2& a, int pred) {
-    asm("{\n.reg .pred q;\nsetp.ne.s32 q, %2, 0;\n@q mov.f32 %0, 0f00000000;\n@q mov.f32 %1, 0f00000000;\n}\n"
-        : "+f"(a.x), "+f"(a.y)
-        : "r"(pred));
-}
-
-__device__ __forceinline__ void red_v4(float2* addr, float2 a, float2 b) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y)
-                 : "memory");
-}
-
-__global__ void __launch_bounds__(CWARPS * 32, RL_CTAS)
-k_gridding_rl(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __restrict__ counter,
-              const float* __restrict__ rec, const float2* __restrict__ ys, long long Mpad, float2* __restrict__ grid) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* ws = smem_raw + warp * GWARP_BYTES;
-    unsigned char* ybuf = ws + 2 * REC_BYTES;
-    float* dummy = reinterpret_cast<float*>(ws + 2 * REC_BYTES + 2 * YS_BYTES);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + 2 * YS_BYTES + 128);
-    const int c = blockIdx.y;
-    float2* gc = grid + (long long)c * g.Kprod;
-    const float2* ysc = ys + (long long)c * Mpad;
-    // lanes 30, 31: group 3 never owns the retiring plane, so whatever they accumulate is never written
-    const int lt = lane / RROWS;
-    const int lr = lane - RROWS * lt;
-    const int KK = g.K1 * g.K2;
-    if (lane == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    // the record that ends every item: first plane = INT_MAX (the phases then only retire what is left)
-    dummy[lane] = lane == 18 ? __int_as_float(INT_MAX) : 0.f;
-    __syncwarp();
-    unsigned gk = 0;
-
-    for (int item = next_item(counter + c, lane); item < n_work; item = next_item(counter + c, lane)) {
-        const WorkItem wi = work[item];
-        const int q1 = wi.tile / g.nq2, q2 = wi.tile - q1 * g.nq2;
-        // this lane's row inside plane 0: columns 0..7 and 8..12 of the box (the periodic wrap falls between them)
-        float2 *pA, *pB;
-        {
-            int row = q1 * RT1 + lr;
-            if (row >= g.K1) row -= g.K1;
-            const int colA = q2 * RT2;
-            int colB = colA + 8;
-            if (colB >= g.K2) colB -= g.K2;
-            float2* rowp = gc + row * g.K2;
-            pA = rowp + colA;
-            pB = rowp + colB;
-        }
-        const int nchunks = (wi.end - wi.begin + CCH - 1) / CCH;
-        auto issue = [&](int k) {      // lane 0 only
-            const int s = wi.begin + k * CCH;
-            const int ns = min(CCH, wi.end - s);
-            const unsigned b = (gk + k) & 1;
-            const int sa = s & ~1;
-            const unsigned yb = (unsigned)(((ns + (s & 1) + 1) & ~1) * 8);
-            mbar_expect(&mbar[b], (unsigned)(ns * CRECW * 4) + yb);
-            tma_bulk(ws + b * REC_BYTES, rec + (long long)s * CRECW, (unsigned)(ns * CRECW * 4), &mbar[b]);
-            tma_bulk(ybuf + b * YS_BYTES, ysc + sa, yb, &mbar[b]);
-        };
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) issue(0);
-
-        P2 A[RCOLS][2];                // [box column][slot of this lane's pair]
-#pragma unroll
-        for (int i = 0; i < RCOLS; ++i) A[i][0] = A[i][1] = make_float2(0.f, 0.f);
-        int kc = 0, u = 0, ns = 0;
-        int K = 0, par = 0;             // slot of the window's first plane, its parity
-        int o0 = 20;                    // record word of this lane's dim-0 weight pair
-        int p = 0, pw = 0, poff = 0;
-        int plim = 0, pnext = 0;
-        bool started = false;
-        const float* Rb = dummy;
-        const float2* Y = reinterpret_cast<const float2*>(dummy);
-
-        // slot 2t holds plane offset j = (2t - K) mod 6: even K -> pair (c0[j], c0[j+1]) at word 20 + j,
-        // odd K -> j odd, pair (c0[j], c0[j+1 mod 6]) at word 26 + j - 1 of the rotated copy
-#define RL_SET_PHASE()                                                                             \
-    {                                                                                              \
-        int jj = 2 * lt - K;                                                                       \
-        if (jj < 0) jj += 6;                                                                       \
-        o0 = (K & 1) ? 25 + jj : 20 + jj;                                                          \
-        if (lt == 3) o0 = 20;                                                                      \
-    }
-#define RL_ACC(CO, I, CV)                                                                          \
-    ffma2_acc(A[CO + I][0], bc2(CV), v0);                                                          \
-    ffma2_acc(A[CO + I][1], bc2(CV), v1);
-#define RL_ACC6(CO)                                                                                \
-    RL_ACC(CO, 0, Ca.x) RL_ACC(CO, 1, Ca.y) RL_ACC(CO, 2, Ca.z) RL_ACC(CO, 3, Ca.w) RL_ACC(CO, 4, Cb.x) RL_ACC(CO, 5, Cb.y)
-#define RL_LOAD(U)                                                                                 \
-    {                                                                                              \
-        const float* R = Rb + (U) * CRECW;                                                         \
-        nCa = *reinterpret_cast<const float4*>(R);                                                 \
-        nCb = *reinterpret_cast<const float4*>(R + 4);                                             \
-        na = R[8 + lr];                                                                            \
-        nW = *reinterpret_cast<const float2*>(R + o0);                                             \
-        nyv = Y[U];                                                                                \
-    }
-    // the registers of sample U were loaded one trip earlier (RL_LOAD); the loads of sample U + 1 go out before the
-    // branch on this sample's column offset (past the end of a run they read this warp's own buffers and are dropped)
-#define RL_SAMPLE(U)                                                                               \
-    {                                                                                              \
-        const float4 Ca = nCa, Cb = nCb;                                                           \
-        const P2 v0 = fmul2(bc2(na * nW.x), nyv), v1 = fmul2(bc2(na * nW.y), nyv);                 \
-        RL_LOAD((U) + 1)                                                                           \
-        switch (__float_as_int(Cb.z)) {                                                            \
-            case 0: RL_ACC6(0) break;                                                              \
-            case 1: RL_ACC6(1) break;                                                              \
-            case 2: RL_ACC6(2) break;                                                              \
-            case 3: RL_ACC6(3) break;                                                              \
-            case 4: RL_ACC6(4) break;                                                              \
-            case 5: RL_ACC6(5) break;                                                              \
-            case 6: RL_ACC6(6) break;                                                              \
-            default: RL_ACC6(7) break;                                                             \
-        }                                                                                          \
-    }
-        // phase PAR: the window's first plane p sits in slot K (parity PAR) of lane group K / 2.  Take every sample
-        // whose first plane is p (the record carries the run length), then retire plane p.
-#define RL_PHASE(PAR)                                                                              \
-    case PAR: {                                                                                    \
-        if (u == ns) { par = PAR; goto chunk_done; }                                               \
-        {                                                                                          \
-            const int2 pr = *reinterpret_cast<const int2*>(Rb + u * CRECW + 18);   /* p0, run */   \
-            pnext = pr.x;                                                                          \
-            if (pnext == p) {                                                                      \
-                int n = min(pr.y, ns - u);                                                         \
-                RL_LOAD(u)                                                                         \
-                _Pragma("unroll 1") for (; n > 0; --n, ++u) RL_SAMPLE(u)                           \
-                plim = p + 5;                                                                      \
-                if (u == ns) { par = PAR; goto chunk_done; }                                       \
-                pnext = __float_as_int(Rb[u * CRECW + 18]);                                        \
-            }                                                                                      \
-        }                                                                                          \
-        {                                                                                          \
-            const int mine = lt == (K >> 1);                                                       \
-            if (mine && !(g.dbg & 1)) {                                                            \
-                float2* a0 = cell_at(pA, poff);                                                    \
-                float2* b0 = cell_at(pB, poff);                                                    \
-                red_v4(a0, A[0][PAR], A[1][PAR]);                                                  \
-                red_v4(a0 + 2, A[2][PAR], A[3][PAR]);                                              \
-                red_v4(a0 + 4, A[4][PAR], A[5][PAR]);                                              \
-                red_v4(a0 + 6, A[6][PAR], A[7][PAR]);                                              \
-                red_v4(b0, A[8][PAR], A[9][PAR]);                                                  \
-                red_v4(b0 + 2, A[10][PAR], A[11][PAR]);                                            \
-                red_v2(b0 + 4, A[12][PAR]);                                                        \
-            }                                                                                      \
-            _Pragma("unroll") for (int i = 0; i < RCOLS; ++i) zero_if(A[i][PAR], mine);            \
-        }                                                                                          \
-        ++p; ++pw; poff += KK;                                                                     \
-        if (pw == g.K0) { pw = 0; poff = 0; }                                                      \
-        K = K == 5 ? 0 : K + 1;                                                                    \
-        if (p > plim) {                 /* nothing left in the window */                           \
-            if (pnext == INT_MAX) goto item_done;                                                  \
-            p = pnext; pw = pnext; poff = pnext * KK; K = pnext % 6;                               \
-            RL_SET_PHASE()                                                                         \
-            par = K & 1;                                                                           \
-            continue;                                                                              \
-        }                                                                                          \
-        RL_SET_PHASE()                                                                             \
-    }
-
-        float4 nCa, nCb;
-        float na;
-        float2 nW;
-        P2 nyv;
-        for (;;) {                      // chunks
-            if (kc == nchunks) {        // all samples taken: the dummy record makes the phases drain the window
-                Rb = dummy;
-                Y = reinterpret_cast<const float2*>(dummy);
-                ns = 1;
-                u = 0;
-            } else {
-                const int s = wi.begin + kc * CCH;
-                const unsigned b = (gk + kc) & 1;
-                if (kc + 1 < nchunks) {
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) issue(kc + 1);
-                }
-                mbar_wait(&mbar[b], ((gk + kc) >> 1) & 1);
-                Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
-                Y = reinterpret_cast<const float2*>(ybuf + b * YS_BYTES) + (s & 1);
-                ns = min(CCH, wi.end - s);
-                u = 0;
-                ++kc;
-            }
-            if (!started) {
-                p = __float_as_int(Rb[18]);
-                K = p % 6;
-                par = K & 1;
-                pw = p;
-                poff = p * KK;
-                plim = p + 5;
-                RL_SET_PHASE()
-                started = true;
-            }
-            for (;;) {                  // planes
-                switch (par) {
-                    RL_PHASE(0)
-                    RL_PHASE(1)
-                }
-                par = 0;
-            }
-        chunk_done:;
-        }
-    item_done:
-        gk += nchunks;
-        __syncwarp();
-    }
-#undef RL_PHASE
-#undef RL_SAMPLE
-#undef RL_LOAD
-#undef RL_ACC6
-#undef RL_ACC
-#undef RL_SET_PHASE
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // grid (de)modulation: grid[g] *= (conj) prod_d m_d[g_d]; one CTA per (g0, g1) row
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_demodulate(float2* __restrict__ grid, const float2* __restrict__ mod, int K0, int K1, int K2) {
@@ -865,11 +612,6 @@ bool col3d_supported(const Geom& g) {
         if (g.J[d] != 6) return false;
     return g.K[0] >= 6 && g.K[1] >= CROWS && g.K[2] >= CCOLS;
 }
-// row-lane scatter: 16-byte REDs on rows of 13 box columns that start at a multiple of 8
-bool rl3d_supported(const Geom& g) {
-    static const bool off = [] { const char* e = getenv("B200NUFFT_NO_RL"); return e && atoi(e) != 0; }();
-    return !off && col3d_supported(g) && g.K[1] >= RROWS && g.K[2] >= 2 * RT2 && g.K[2] % RT2 == 0;
-}
 // the gather's register ring runs two planes ahead of the window: planes up to K0 + 7 are wrapped with one subtraction
 bool col3d_interp_supported(const Geom& g) { return col3d_supported(g) && g.K[0] >= IRING; }
 
@@ -899,7 +641,6 @@ static int col_attrs(b200nufft_plan_t p) {
     if (!p->attr_col) {
         CUDA_TRY(cudaFuncSetAttribute(k_gridding_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_interp_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * IWARP_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(k_gridding_rl, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
         p->attr_col = true;
     }
     return B200_OK;
@@ -966,25 +707,14 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
     // float4 stores need a 16-byte aligned grid and an even element count; otherwise plain memset
     const bool vec = (reinterpret_cast<uintptr_t>(grid) & 15) == 0 && (nel & 1) == 0;
     if (!vec) CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * nel, st));
-    // the row-lane kernel flushes with 16-byte REDs: every coil's grid must start on a 16-byte boundary
-    const bool rl = p->has_rl && p->n_bwork > 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0 && (p->g.Kprod & 1) == 0;
     {
         // sized from the larger of the two jobs (grid zero-fill, data gather), capped: grid-stride loops inside
         const int TB = 256;
         const long long want = std::max<long long>((p->M + TB - 1) / TB, vec ? (nel / 2 + TB * 8 - 1) / (TB * 8) : 1);
         const unsigned nblk = (unsigned)std::min<long long>(std::max<long long>(want, 1), 148LL * 64);
-        k_gather_sorted_col<<<nblk, TB, 0, st>>>(rl ? p->d_bside : p->d_cside, p->M, Mpad, y, p->d_ys2, nb,
+        k_gather_sorted_col<<<nblk, TB, 0, st>>>(p->d_cside, p->M, Mpad, y, p->d_ys2, nb,
                                                  reinterpret_cast<float4*>(grid), vec ? nel / 2 : 0, p->d_ccount);
         LAUNCH_CHECK();
-    }
-    if (rl) {
-        ColGeom cg = col_geom(p->g);
-        cg.nq2 = (p->g.K[2] + RT2 - 1) / RT2;
-        dim3 gr((unsigned)std::min((p->n_bwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, RL_CTAS)), nb);
-        k_gridding_rl<<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(cg, p->d_bwork, p->n_bwork, p->d_ccount, p->d_brec,
-                                                                    p->d_ys2, Mpad, grid);
-        LAUNCH_CHECK();
-        return B200_OK;
     }
     dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, COL_S_CTAS)), nb);
     k_gridding_col<<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,

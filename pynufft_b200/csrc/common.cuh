@@ -127,7 +127,6 @@ struct PlanConst {
 // column-sweep gridding (col3d.cu): 4 x 5 cross-section columns of first-neighbour cells swept along dim 0;
 // 32-word sample records in sweep order
 constexpr int COL_T1 = 4, COL_T2 = 5, COL_RECW = 32, COL_SEG = 320;
-constexpr int RL_T1 = 5, RL_T2 = 8;     // row-lane scatter (col3d.cu k_gridding_rl): 5 x 8 columns, 10 x 13 box
 // 2-D multi-coil row sweep (sweep2d.cu): strips of SW2_CT first-neighbour columns (dim 1) swept along dim 0, coil on the
 // lanes; 20-word sample records in sweep order
 constexpr int SW2_CT = 3, SW2_RECW = 20, SW2_SEG = 64;
@@ -168,13 +167,6 @@ struct b200nufft_plan_s {
     float4* d_cside = nullptr;      // (M,) (P''.re, P''.im, original index, 0) in sweep order
     WorkItem* d_cwork = nullptr;    // (column, begin, end) segments of at most COL_SEG samples
     int n_cwork = 0;
-    // row-lane scatter (col3d.cu k_gridding_rl): the same for 5 x 4 columns
-    bool has_rl = false;
-    int* d_bperm = nullptr;
-    float* d_brec = nullptr;
-    float4* d_bside = nullptr;
-    WorkItem* d_bwork = nullptr;
-    int n_bwork = 0;
     // 2-D multi-coil row sweep (2-D, J = 6; sweep2d.cu): samples sorted by (strip, first row), batch-innermost grids
     bool has_sw2 = false;
     int* d_sw_perm = nullptr;       // (M,) sweep-order permutation (parity export)
@@ -249,7 +241,6 @@ int ensure_scratch(b200nufft_plan_t p, int nb);
 int ensure_scratch2(b200nufft_plan_t p, int nb);
 // col3d.cu: register-resident column-sweep gridding (3-D, J = 6); the grid it produces is phase-modulated
 bool col3d_supported(const Geom& g);
-bool rl3d_supported(const Geom& g);
 // zeroes the grid itself (inside its pre-pass kernel)
 int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st);
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st);

@@ -173,7 +173,7 @@ __global__ void k_build_records(Geom g, const PlanConst* __restrict__ pc,
 // side: (P''.re, P''.im, original index, 0), P'' = prod_d exp(i (om N/2 - s dk - s (k0' - 1))): the per-offset phase
 // exp(i s (j+1)) of the reference coefficient (helper.py:148-162) is carried by the modulated grid.
 __global__ void k_col_keys(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om, long long M,
-                           int T1, int T2, int nq2, int* __restrict__ keys, int* __restrict__ vals) {
+                           int nq2, int* __restrict__ keys, int* __restrict__ vals) {
     long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (m >= M) return;
     int ks[3];
@@ -181,15 +181,12 @@ __global__ void k_col_keys(Geom g, const PlanConst* __restrict__ pc, const doubl
         double q;
         ks[d] = wrap_index(offset_k0(om[m * 3 + d], pc->gam[d], g.J[d], &q) + 1, g.K[d]);
     }
-    keys[m] = ((ks[1] / T1) * nq2 + ks[2] / T2) * g.K[0] + ks[0];
+    keys[m] = ((ks[1] / COL_T1) * nq2 + ks[2] / COL_T2) * g.K[0] + ks[0];
     vals[m] = (int)m;
 }
 
-// kind 1: the row-lane scatter's records (col3d.cu k_gridding_rl), columns of RL_T1 x RL_T2, box 10 rows x 13 columns:
-//   [c2[0..5] | coff - | c1pad[0..9] | p0 run | c0[0..5] | c0[1..5] c0[0]],  coff = first box column of the footprint,
-//   c1pad[b] = c1[b - k1rel] (zero outside the footprint): box rows; same sign folding, same side array
 __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const double* __restrict__ om,
-                              const int* __restrict__ perm, long long M, int kind, int nq2, const int* __restrict__ cbin,
+                              const int* __restrict__ perm, long long M, int nq2, const int* __restrict__ cbin,
                               float* __restrict__ rec, float4* __restrict__ side) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -208,16 +205,7 @@ __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const do
         const float sgd = ((g.N[d] - 1) & 1) ? -1.f : 1.f;
         for (int j = 0; j < 6; ++j) {
             const float cj = (k + j >= g.K[d]) ? sgd * (float)R.c[j] : (float)R.c[j];
-            if (kind == 1) {
-                if (d == 0) {
-                    out[20 + j] = cj;                  // plane k + j
-                    out[26 + (j + 5) % 6] = cj;        // rotated copy: word 26 + j - 1
-                } else if (d == 1) {
-                    out[8 + k % RL_T1 + j] = cj;       // box row 0..9
-                } else {
-                    out[j] = cj;                       // footprint column j (box column coff + j)
-                }
-            } else if (d == 0) {
+            if (d == 0) {
                 out[12 + j] = cj;                      // plane k + j
             } else if (d == 1) {
                 const int b = k % COL_T1 + j;          // box row 0..8
@@ -229,11 +217,9 @@ __global__ void k_col_records(Geom g, const PlanConst* __restrict__ pc, const do
         const double s = pc->gam[d] * ((double)g.N[d] - 1.0) / 2.0;
         ph += o * (double)g.N[d] / 2.0 - s * R.dk - s * (double)(k - 1);
     }
-    const int T1 = kind == 1 ? RL_T1 : COL_T1, T2 = kind == 1 ? RL_T2 : COL_T2;
-    const int key = ((ks[1] / T1) * nq2 + ks[2] / T2) * g.K[0] + ks[0];
+    const int key = ((ks[1] / COL_T1) * nq2 + ks[2] / COL_T2) * g.K[0] + ks[0];
     outi[18] = ks[0];
     outi[19] = cbin[key + 1] - (int)i;
-    if (kind == 1) outi[6] = ks[2] % RL_T2;
     double sn, cs;
     sincos(ph, &sn, &cs);
     side[i] = make_float4((float)cs, (float)sn, __int_as_float(m), 0.f);
@@ -576,24 +562,15 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
     }
 
     // ---- column-sweep gridding: second sort by (column, first plane), records, work items ----
-    // kind 0: 4 x 5 columns (k_gridding_col, k_interp_col); kind 1: 5 x 4 columns of the row-lane scatter (k_gridding_rl)
-    p->has_rl = p->has_col && M > 0 && rl3d_supported(g);
-    for (int kind = 0; kind < 2 && p->has_col && M > 0; ++kind) {
-        if (kind == 1 && !p->has_rl) break;
-        const int T1 = kind == 1 ? RL_T1 : COL_T1, T2 = kind == 1 ? RL_T2 : COL_T2;
-        int*& o_perm = kind == 1 ? p->d_bperm : p->d_cperm;
-        float*& o_rec = kind == 1 ? p->d_brec : p->d_crec;
-        float4*& o_side = kind == 1 ? p->d_bside : p->d_cside;
-        WorkItem*& o_work = kind == 1 ? p->d_bwork : p->d_cwork;
-        int& o_nwork = kind == 1 ? p->n_bwork : p->n_cwork;
-        const int col_nq1 = (g.K[1] + T1 - 1) / T1, col_nq2 = (g.K[2] + T2 - 1) / T2;
+    if (p->has_col && M > 0) {
+        const int col_nq1 = (g.K[1] + COL_T1 - 1) / COL_T1, col_nq2 = (g.K[2] + COL_T2 - 1) / COL_T2;
         const int col_ncol = col_nq1 * col_nq2;
         const int n_cbins = col_ncol * g.K[0];               // bins = (column, first plane)
-        PLAN_TRY(cudaMalloc(&o_perm, sizeof(int) * M));
-        PLAN_TRY(cudaMalloc(&o_rec, sizeof(float) * M * COL_RECW));
-        PLAN_TRY(cudaMalloc(&o_side, sizeof(float4) * M));
+        PLAN_TRY(cudaMalloc(&p->d_cperm, sizeof(int) * M));
+        PLAN_TRY(cudaMalloc(&p->d_crec, sizeof(float) * M * COL_RECW));
+        PLAN_TRY(cudaMalloc(&p->d_cside, sizeof(float4) * M));
         p->bytes += sizeof(int) * M + sizeof(float) * M * COL_RECW + sizeof(float4) * M;
-        if (kind == 0) {   // modulation tables m_d[g] = exp(i s_d g), s_d = gam_d (N_d - 1) / 2
+        {   // modulation tables m_d[g] = exp(i s_d g), s_d = gam_d (N_d - 1) / 2
             std::vector<float2> hm(g.K[0] + g.K[1] + g.K[2]);
             int o = 0;
             for (int d = 0; d < 3; ++d) {
@@ -613,21 +590,21 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
         int *d_keys = t_keys.as<int>(), *d_keys_s = t_keys_s.as<int>(), *d_vals = t_vals.as<int>(), *d_cbin = t_cbin.as<int>();
         const int TB = 256;
         const unsigned nblk = (unsigned)((M + TB - 1) / TB);
-        k_col_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, T1, T2, col_nq2, d_keys, d_vals);
+        k_col_keys<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, M, col_nq2, d_keys, d_vals);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         int end_bit = 1;
         while ((1LL << end_bit) < n_cbins) ++end_bit;
         size_t tmp_bytes = 0;
-        PLAN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_vals, o_perm, (int)M, 0,
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_cperm, (int)M, 0,
                                                  end_bit, st));
         PLAN_TRY(cudaMalloc(&t_tmp.p, tmp_bytes));
-        PLAN_TRY(cub::DeviceRadixSort::SortPairs(t_tmp.p, tmp_bytes, d_keys, d_keys_s, d_vals, o_perm, (int)M, 0,
+        PLAN_TRY(cub::DeviceRadixSort::SortPairs(t_tmp.p, tmp_bytes, d_keys, d_keys_s, d_vals, p->d_cperm, (int)M, 0,
                                                  end_bit, st));
         k_bin_start<<<(n_cbins + 1 + TB - 1) / TB, TB, 0, st>>>(d_keys_s, M, n_cbins, d_cbin);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
-        k_col_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, o_perm, M, kind, col_nq2, d_cbin, o_rec, o_side);
+        k_col_records<<<nblk, TB, 0, st>>>(g, p->d_pc, p->d_om, p->d_cperm, M, col_nq2, d_cbin, p->d_crec, p->d_cside);
         g_launches++;
         PLAN_TRY(cudaGetLastError());
         std::vector<int> h_cbin(n_cbins + 1, 0);
@@ -650,13 +627,14 @@ extern "C" int b200nufft_plan_create(b200nufft_plan_t* out, int device, int ndim
                 if (se > sb) cw.push_back(WorkItem{col, sb, se, 0});
             }
         }
-        o_nwork = (int)cw.size();
-        PLAN_TRY(cudaMalloc(&o_work, sizeof(WorkItem) * cw.size()));
-        PLAN_TRY(cudaMemcpyAsync(o_work, cw.data(), sizeof(WorkItem) * cw.size(), cudaMemcpyHostToDevice, st));
+        p->n_cwork = (int)cw.size();
+        PLAN_TRY(cudaMalloc(&p->d_cwork, sizeof(WorkItem) * cw.size()));
+        PLAN_TRY(cudaMemcpyAsync(p->d_cwork, cw.data(), sizeof(WorkItem) * cw.size(), cudaMemcpyHostToDevice, st));
         PLAN_TRY(cudaStreamSynchronize(st));
         p->bytes += sizeof(WorkItem) * cw.size();
+    } else {
+        p->has_col = false;
     }
-    if (!(p->has_col && M > 0)) p->has_col = false;
     // ---- 2-D multi-coil row sweep: sort by (strip, first row), records, work items, modulation tables ----
     p->has_sw2 = sweep2d_supported(g) && M > 0;
     if (p->has_sw2) {
@@ -750,10 +728,6 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_crec);
     cudaFree(p->d_cside);
     cudaFree(p->d_cwork);
-    cudaFree(p->d_bperm);
-    cudaFree(p->d_brec);
-    cudaFree(p->d_bside);
-    cudaFree(p->d_bwork);
     cudaFree(p->d_sw_perm);
     cudaFree(p->d_sw_rec);
     cudaFree(p->d_sw_work);

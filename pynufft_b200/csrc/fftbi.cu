@@ -69,6 +69,11 @@ __device__ __forceinline__ void dft8(float2 (&v)[8]) {
     v[7] = make_float2(e3.x - o3.x, e3.y - o3.y);
 }
 
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 struct BiPass {
     const float2* in;       // grid, or the image for the forward pass A
     float2* out;            // grid, or the image for the inverse pass B'
@@ -152,31 +157,37 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
     const bool cact = cb + c < a.nb;
     const int line = blockIdx.x;
     for (int i = t; i < N; i += FTB) tw[i] = __ldg(a.tw + i);
-    // ---- load (natural order) ----
+    // ---- load (natural order): every element of the line goes global -> shared memory by an 8-byte cp.async, so that
+    //      all loads of the CTA are in flight at once (through registers the load phase was a chain of DRAM round
+    //      trips: `long_scoreboard` was the top stall of these passes) ----
     if (a.mode == 1) {
-        const float s0 = a.apply_sn ? a.sn_other[line] : 1.f;
+        // image -> grid: the coil-dependent factor (coil map, or the multi-coil image) is copied, then scaled in place
         const long long nrow = (long long)line * a.Nline;
-#pragma unroll 4
+        const float2* src = a.sens ? a.sens : (a.x_single ? nullptr : a.in);
         for (int i = gi; i < N; i += FTB / NCO) {
-            float2 v = make_float2(0.f, 0.f);
-            if (i < a.nin && cact) {
-                const long long n = nrow + i;
-                float2 xv = a.x_single ? a.in[n] : a.in[n * a.nb + cb + c];
-                if (a.sens) xv = cmul(xv, a.sens[n * a.nb + cb + c]);
-                const float f = a.apply_sn ? s0 * a.sn_line[i] : 1.f;
-                v = make_float2(xv.x * f, xv.y * f);
-            }
-            buf[i * NCO + c] = v;
+            float2* d = buf + i * NCO + c;
+            if (i < a.nin && cact && src) cp_async8(d, src + (nrow + i) * a.nb + cb + c);
+            else *d = make_float2(i < a.nin && cact ? 1.f : 0.f, 0.f);
+        }
+        cp_async_wait_all();
+        const float s0 = a.apply_sn ? a.sn_other[line] : 1.f;
+        for (int i = gi; i < a.nin; i += FTB / NCO) {
+            float2* d = buf + i * NCO + c;
+            float2 v = *d;
+            if (a.x_single && a.sens) v = cmul(v, __ldg(a.in + nrow + i));
+            else if (a.x_single) v = __ldg(a.in + nrow + i);
+            const float f = a.apply_sn ? s0 * a.sn_line[i] : 1.f;
+            *d = cact ? make_float2(v.x * f, v.y * f) : make_float2(0.f, 0.f);
         }
     } else {
         const float2* src = a.in + (long long)line * a.lstride * a.nb + cb + c;
         const long long es = a.estride * a.nb;
-#pragma unroll 8
         for (int i = gi; i < N; i += FTB / NCO) {
-            float2 v = make_float2(0.f, 0.f);
-            if (i < a.nin && cact) v = __ldg(src + i * es);
-            buf[i * NCO + c] = v;
+            float2* d = buf + i * NCO + c;
+            if (i < a.nin && cact) cp_async8(d, src + i * es);
+            else *d = make_float2(0.f, 0.f);
         }
+        cp_async_wait_all();
     }
     __syncthreads();
     stages<DIR, LOGN>(buf, tw, c, gi);

@@ -153,13 +153,20 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
     float2* buf = reinterpret_cast<float2*>(fsm);                       // [N][NCO]
     float2* tw = buf + N * NCO;                                         // [N]
     const int t = threadIdx.x, c = t & (NCO - 1), gi = t >> 4;          // coil inside the block, butterfly group
+    const int line = blockIdx.x;
+    float2* aux = tw + N;                                               // [N]: per-point factors of the image side
+    int* rv = reinterpret_cast<int*>(aux + N);                          // [N]: digit-reversal table
+    float* fsv = reinterpret_cast<float*>(aux);                         // mode 2: real factors
+    for (int i = t; i < N; i += FTB) {
+        tw[i] = __ldg(a.tw + i);
+        rv[i] = __ldg(a.rev + i);
+    }
     const int cb = blockIdx.y * NCO;
     const bool cact = cb + c < a.nb;
-    const int line = blockIdx.x;
-    for (int i = t; i < N; i += FTB) tw[i] = __ldg(a.tw + i);
     // ---- load (natural order): every element of the line goes global -> shared memory by an 8-byte cp.async, so that
     //      all loads of the CTA are in flight at once (through registers the load phase was a chain of DRAM round
-    //      trips: `long_scoreboard` was the top stall of these passes) ----
+    //      trips: `long_scoreboard` was the top stall of these passes); the per-point factors of the image side are
+    //      gathered into shared memory while the copies fly ----
     if (a.mode == 1) {
         // image -> grid: the coil-dependent factor (coil map, or the multi-coil image) is copied, then scaled in place
         const long long nrow = (long long)line * a.Nline;
@@ -169,15 +176,18 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
             if (i < a.nin && cact && src) cp_async8(d, src + (nrow + i) * a.nb + cb + c);
             else *d = make_float2(i < a.nin && cact ? 1.f : 0.f, 0.f);
         }
-        cp_async_wait_all();
         const float s0 = a.apply_sn ? a.sn_other[line] : 1.f;
+        for (int i = t; i < a.nin; i += FTB) {              // aux[i] = [x[i]] * sn: the same for every coil
+            const float f = a.apply_sn ? s0 * a.sn_line[i] : 1.f;
+            const float2 xv = a.x_single ? __ldg(a.in + nrow + i) : make_float2(1.f, 0.f);
+            aux[i] = make_float2(xv.x * f, xv.y * f);
+        }
+        cp_async_wait_all();
+        __syncthreads();
         for (int i = gi; i < a.nin; i += FTB / NCO) {
             float2* d = buf + i * NCO + c;
-            float2 v = *d;
-            if (a.x_single && a.sens) v = cmul(v, __ldg(a.in + nrow + i));
-            else if (a.x_single) v = __ldg(a.in + nrow + i);
-            const float f = a.apply_sn ? s0 * a.sn_line[i] : 1.f;
-            *d = cact ? make_float2(v.x * f, v.y * f) : make_float2(0.f, 0.f);
+            const float2 v = cmul(*d, aux[i]);
+            *d = cact ? v : make_float2(0.f, 0.f);
         }
     } else {
         const float2* src = a.in + (long long)line * a.lstride * a.nb + cb + c;
@@ -187,22 +197,28 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
             if (i < a.nin && cact) cp_async8(d, src + i * es);
             else *d = make_float2(0.f, 0.f);
         }
+        if (a.mode == 2) {                                  // fsv[f] = scale * (sn | 1 / sn) of image column f
+            const float s0 = a.sn_other[line];
+            for (int f = t; f < a.nout; f += FTB) {
+                float fs = a.scale;
+                const float sv = s0 * a.sn_line[f];
+                if (a.apply_sn == 1) fs *= sv;
+                if (a.apply_sn == 2) fs /= sv;
+                fsv[f] = fs;
+            }
+        }
         cp_async_wait_all();
     }
     __syncthreads();
     stages<DIR, LOGN>(buf, tw, c, gi);
     // ---- store: position pos holds frequency rev[pos] ----
     if (a.mode == 2) {
-        const float s0 = a.sn_other[line];
         const long long nrow = (long long)line * a.Nline;
 #pragma unroll 4
         for (int pos = gi; pos < N; pos += FTB / NCO) {
-            const int f = __ldg(a.rev + pos);
+            const int f = rv[pos];
             if (f < a.nout && cact) {
-                float fs = a.scale;
-                const float sv = s0 * a.sn_line[f];
-                if (a.apply_sn == 1) fs *= sv;
-                if (a.apply_sn == 2) fs /= sv;
+                const float fs = fsv[f];
                 const float2 v = buf[pos * NCO + c];
                 a.out[(nrow + f) * a.nb + cb + c] = make_float2(v.x * fs, v.y * fs);
             }
@@ -212,11 +228,14 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
         const long long es = a.estride * a.nb;
 #pragma unroll 8
         for (int pos = gi; pos < N; pos += FTB / NCO) {
-            const int f = __ldg(a.rev + pos);
+            const int f = rv[pos];
             if (f < a.nout && cact) dst[f * es] = buf[pos * NCO + c];
         }
     }
 }
+
+// line buffer [n][NCO] + twiddles [n] + image-side factors [n] (float2 each) + digit-reversal table [n] (int)
+size_t fbi_smem(int n) { return sizeof(float2) * (size_t)n * (NCO + 2) + sizeof(int) * (size_t)n; }
 
 bool pow2_ok(int k) { return k >= 64 && k <= 1024 && (k & (k - 1)) == 0; }
 
@@ -270,7 +289,7 @@ static int ensure_tables(b200nufft_plan_t p) {
     CUDA_TRY(cudaMalloc(&p->d_fbi_rev, sizeof(int) * rev.size()));
     CUDA_TRY(cudaMemcpy(p->d_fbi_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(p->d_fbi_rev, rev.data(), sizeof(int) * rev.size(), cudaMemcpyHostToDevice));
-    const int smem = (int)(sizeof(float2) * 1024 * (NCO + 1));
+    const int smem = (int)fbi_smem(1024);
 #define FBI_ATTR(LG)                                                                                         \
     CUDA_TRY(cudaFuncSetAttribute(k_fftbi<-1, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));     \
     CUDA_TRY(cudaFuncSetAttribute(k_fftbi<1, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -296,11 +315,11 @@ static BiPass base_pass(b200nufft_plan_t p, int dim, int nb) {
 template <int DIR>
 static int launch(const BiPass& a, int nlines, int nb, cudaStream_t st) {
     dim3 gr((unsigned)nlines, (unsigned)((nb + NCO - 1) / NCO));
-    size_t smem = sizeof(float2) * (size_t)a.n * (NCO + 1);
+    size_t smem = fbi_smem(a.n);
     // tuning knob: resident CTAs per SM (more shared memory per CTA = fewer of them); the number of lines is fixed, so
     // the best occupancy is the one that makes the number of waves an integer
     static const int want_ctas = [] { const char* e = getenv("B200NUFFT_FBI_CTAS"); return e ? atoi(e) : 0; }();
-    if (want_ctas > 0) smem = std::max(smem, std::min<size_t>((size_t)(227 * 1024) / want_ctas - 1024, sizeof(float2) * 1024 * (NCO + 1)));
+    if (want_ctas > 0) smem = std::max(smem, std::min<size_t>((size_t)(227 * 1024) / want_ctas - 1024, fbi_smem(1024)));
     switch (a.n) {
         case 64: k_fftbi<DIR, 6><<<gr, FTB, smem, st>>>(a); break;
         case 128: k_fftbi<DIR, 7><<<gr, FTB, smem, st>>>(a); break;

@@ -33,21 +33,52 @@ __device__ __forceinline__ void block_reduce_add2(double re, double im, double* 
     }
 }
 
-__global__ void __launch_bounds__(RED_TB) k_dotc(const float2* __restrict__ a, const float2* __restrict__ b,
-                                                 long long n, double* __restrict__ out) {
-    float re = 0.f, im = 0.f;
-    double dre = 0.0, dim_ = 0.0;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    int cnt = 0;
-    for (; i < n; i += stride) {
-        float2 x = a[i], y = b[i];
-        re = fmaf(x.x, y.x, fmaf(x.y, y.y, re));
-        im = fmaf(x.x, y.y, fmaf(-x.y, y.x, im));
-        if (++cnt == 64) { dre += re; dim_ += im; re = im = 0.f; cnt = 0; }   // bounded f32 partials
+// ---- streaming skeleton -------------------------------------------------------------------------------------------
+// The vector kernels below walk n complex elements in 16-byte pieces (two elements), SU pieces per thread in flight:
+// all loads of a trip are issued before the first use (with one 8-byte load per trip the kernels sat at 4.4 - 5.6 TB/s
+// of the 6.5 TB/s copy bandwidth).  n4 = number of 16-byte pieces (0 when a pointer is not 16-byte aligned); the
+// elements from 2 * n4 on are done one by one.
+constexpr int SU = 4;
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 pack4(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define STREAM_LOOP(N4, PIECES, SINGLE)                                                            \
+    {                                                                                              \
+        const long long stride = (long long)gridDim.x * blockDim.x;                               \
+        long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;                           \
+        for (; i + (SU - 1) * stride < (N4); i += SU * stride) { PIECES(SU) }                      \
+        for (; i < (N4); i += stride) { PIECES(1) }                                                \
+        for (long long j = 2 * (N4) + blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += stride) { SINGLE }  \
     }
-    dre += re;
-    dim_ += im;
+
+__device__ __forceinline__ void dot_acc(float2 x, float2 y, float& re, float& im) {
+    re = fmaf(x.x, y.x, fmaf(x.y, y.y, re));
+    im = fmaf(x.x, y.y, fmaf(-x.y, y.x, im));
+}
+
+__global__ void __launch_bounds__(RED_TB) k_dotc(const float2* __restrict__ a, const float2* __restrict__ b,
+                                                 long long n, long long n4, double* __restrict__ out) {
+    double dre = 0.0, dim_ = 0.0;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+#define DOT_PIECES(U)                                                                              \
+    float4 xv[U], yv[U];                                                                           \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) { xv[u] = a4[i + u * stride]; yv[u] = b4[i + u * stride]; }  \
+    float re = 0.f, im = 0.f;                       /* bounded f32 partials: 2 U elements */        \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                                \
+        dot_acc(lo2(xv[u]), lo2(yv[u]), re, im);                                                   \
+        dot_acc(hi2(xv[u]), hi2(yv[u]), re, im);                                                   \
+    }                                                                                              \
+    dre += re; dim_ += im;
+#define DOT_SINGLE                                                                                 \
+    float re = 0.f, im = 0.f;                                                                      \
+    dot_acc(a[j], b[j], re, im);                                                                   \
+    dre += re; dim_ += im;
+    STREAM_LOOP(n4, DOT_PIECES, DOT_SINGLE)
+#undef DOT_PIECES
+#undef DOT_SINGLE
     block_reduce_add2(dre, dim_, out);
 }
 
@@ -57,60 +88,95 @@ __device__ __forceinline__ float2 cdivd(const double* num, const double* den) { 
     return make_float2((float)((a * c + b * d) / m), (float)((b * c - a * d) / m));
 }
 
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float nrm2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+
+// r = b - Ax ; p = r ; rsold += sum |r|^2
 __global__ void __launch_bounds__(RED_TB)
 k_cg_init(const float2* __restrict__ b, const float2* __restrict__ Ax, float2* __restrict__ r,
-          float2* __restrict__ p, double* __restrict__ rsold, long long n) {
+          float2* __restrict__ p, double* __restrict__ rsold, long long n, long long n4) {
     double dre = 0.0;
-    float re = 0.f;
-    int cnt = 0;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        float2 bv = b[i], av = Ax[i];
-        float2 rv = make_float2(bv.x - av.x, bv.y - av.y);
-        r[i] = rv;
-        p[i] = rv;
-        re = fmaf(rv.x, rv.x, fmaf(rv.y, rv.y, re));
-        if (++cnt == 64) { dre += re; re = 0.f; cnt = 0; }
-    }
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    const float4* A4 = reinterpret_cast<const float4*>(Ax);
+    float4* r4 = reinterpret_cast<float4*>(r);
+    float4* p4 = reinterpret_cast<float4*>(p);
+#define INIT_PIECES(U)                                                                             \
+    float4 bv[U], av[U];                                                                           \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) { bv[u] = b4[i + u * stride]; av[u] = A4[i + u * stride]; }  \
+    float re = 0.f;                                                                                \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                                \
+        const float2 r0 = sub2(lo2(bv[u]), lo2(av[u])), r1 = sub2(hi2(bv[u]), hi2(av[u]));         \
+        const float4 rv = pack4(r0, r1);                                                           \
+        r4[i + u * stride] = rv;                                                                   \
+        p4[i + u * stride] = rv;                                                                   \
+        re += nrm2(r0) + nrm2(r1);                                                                 \
+    }                                                                                              \
     dre += re;
+#define INIT_SINGLE                                                                                \
+    const float2 rv = sub2(b[j], Ax[j]);                                                           \
+    r[j] = rv;                                                                                     \
+    p[j] = rv;                                                                                     \
+    dre += nrm2(rv);
+    STREAM_LOOP(n4, INIT_PIECES, INIT_SINGLE)
+#undef INIT_PIECES
+#undef INIT_SINGLE
     block_reduce_add2(dre, 0.0, rsold);
 }
 
+// alpha = rsold / pAp ; x += alpha p ; r -= alpha Ap ; rsnew += sum |r|^2
 __global__ void __launch_bounds__(RED_TB)
 k_cg_update_xr(float2* __restrict__ x, float2* __restrict__ r, const float2* __restrict__ p,
                const float2* __restrict__ Ap, const double* __restrict__ rsold, const double* __restrict__ pAp,
-               double* __restrict__ rsnew, long long n) {
+               double* __restrict__ rsnew, long long n, long long n4) {
     const float2 alpha = cdivd(rsold, pAp);
     double dre = 0.0;
-    float re = 0.f;
-    int cnt = 0;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        float2 pv = p[i], qv = Ap[i], xv = x[i], rv = r[i];
-        float2 ap = cmul(alpha, pv), aq = cmul(alpha, qv);
-        xv.x += ap.x; xv.y += ap.y;
-        rv.x -= aq.x; rv.y -= aq.y;
-        x[i] = xv;
-        r[i] = rv;
-        re = fmaf(rv.x, rv.x, fmaf(rv.y, rv.y, re));
-        if (++cnt == 64) { dre += re; re = 0.f; cnt = 0; }
-    }
+    float4* x4 = reinterpret_cast<float4*>(x);
+    float4* r4 = reinterpret_cast<float4*>(r);
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    const float4* q4 = reinterpret_cast<const float4*>(Ap);
+#define XR_PIECES(U)                                                                               \
+    float4 pv[U], qv[U], xv[U], rv[U];                                                             \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                                \
+        pv[u] = p4[i + u * stride]; qv[u] = q4[i + u * stride];                                    \
+        xv[u] = x4[i + u * stride]; rv[u] = r4[i + u * stride];                                    \
+    }                                                                                              \
+    float re = 0.f;                                                                                \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                                \
+        const float2 x0 = add2(lo2(xv[u]), cmul(alpha, lo2(pv[u]))), x1 = add2(hi2(xv[u]), cmul(alpha, hi2(pv[u]))); \
+        const float2 r0 = sub2(lo2(rv[u]), cmul(alpha, lo2(qv[u]))), r1 = sub2(hi2(rv[u]), cmul(alpha, hi2(qv[u]))); \
+        x4[i + u * stride] = pack4(x0, x1);                                                        \
+        r4[i + u * stride] = pack4(r0, r1);                                                        \
+        re += nrm2(r0) + nrm2(r1);                                                                 \
+    }                                                                                              \
     dre += re;
+#define XR_SINGLE                                                                                  \
+    const float2 x0 = add2(x[j], cmul(alpha, p[j])), r0 = sub2(r[j], cmul(alpha, Ap[j]));          \
+    x[j] = x0;                                                                                     \
+    r[j] = r0;                                                                                     \
+    dre += nrm2(r0);
+    STREAM_LOOP(n4, XR_PIECES, XR_SINGLE)
+#undef XR_PIECES
+#undef XR_SINGLE
     block_reduce_add2(dre, 0.0, rsnew);
 }
 
-__global__ void k_cg_update_p(float2* __restrict__ p, const float2* __restrict__ r,
-                              const double* __restrict__ rsnew, const double* __restrict__ rsold, long long n) {
+// beta = rsnew / rsold ; p = r + beta p
+__global__ void __launch_bounds__(RED_TB)
+k_cg_update_p(float2* __restrict__ p, const float2* __restrict__ r, const double* __restrict__ rsnew,
+              const double* __restrict__ rsold, long long n, long long n4) {
     const float2 beta = cdivd(rsnew, rsold);
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        float2 bp = cmul(beta, p[i]);
-        float2 rv = r[i];
-        p[i] = make_float2(rv.x + bp.x, rv.y + bp.y);
-    }
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* r4 = reinterpret_cast<const float4*>(r);
+#define P_PIECES(U)                                                                                \
+    float4 pv[U], rv[U];                                                                           \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) { pv[u] = p4[i + u * stride]; rv[u] = r4[i + u * stride]; }  \
+    _Pragma("unroll") for (int u = 0; u < U; ++u)                                                  \
+        p4[i + u * stride] = pack4(add2(lo2(rv[u]), cmul(beta, lo2(pv[u]))), add2(hi2(rv[u]), cmul(beta, hi2(pv[u]))));
+#define P_SINGLE p[j] = add2(r[j], cmul(beta, p[j]));
+    STREAM_LOOP(n4, P_PIECES, P_SINGLE)
+#undef P_PIECES
+#undef P_SINGLE
 }
 
 __global__ void k_cdiv(float2* __restrict__ a, const float2* __restrict__ b, long long n) {
@@ -132,18 +198,29 @@ __global__ void k_cmul(float2* __restrict__ a, const float2* __restrict__ b, lon
 // out = a x + b y with host scalars (the vector updates of the Krylov recurrences, pynufft_b200/krylov.py);
 // HAS_Y = false: out = a x and y is never read.  out may alias x or y.
 template <bool HAS_Y>
-__global__ void k_axpby(float2* out, float2 a, const float2* x, float2 b, const float2* y, long long n) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        float2 r = cmul(a, x[i]);
-        if (HAS_Y) {
-            const float2 t = cmul(b, y[i]);
-            r.x += t.x;
-            r.y += t.y;
-        }
-        out[i] = r;
+__global__ void __launch_bounds__(RED_TB)
+k_axpby(float2* out, float2 a, const float2* x, float2 b, const float2* y, long long n, long long n4) {
+    float4* o4 = reinterpret_cast<float4*>(out);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+#define AX_PIECES(U)                                                                               \
+    float4 xv[U], yv[U];                                                                           \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                                \
+        xv[u] = x4[i + u * stride];                                                                \
+        if (HAS_Y) yv[u] = y4[i + u * stride];                                                     \
+    }                                                                                              \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {                                                \
+        float2 r0 = cmul(a, lo2(xv[u])), r1 = cmul(a, hi2(xv[u]));                                 \
+        if (HAS_Y) { r0 = add2(r0, cmul(b, lo2(yv[u]))); r1 = add2(r1, cmul(b, hi2(yv[u]))); }     \
+        o4[i + u * stride] = pack4(r0, r1);                                                        \
     }
+#define AX_SINGLE                                                                                  \
+    float2 r0 = cmul(a, x[j]);                                                                     \
+    if (HAS_Y) r0 = add2(r0, cmul(b, y[j]));                                                       \
+    out[j] = r0;
+    STREAM_LOOP(n4, AX_PIECES, AX_SINGLE)
+#undef AX_PIECES
+#undef AX_SINGLE
 }
 
 // ---- L1TVOLS ---------------------------------------------------------------------------------
@@ -259,8 +336,9 @@ extern "C" int b200nufft_zero_scalars(double* s, int n, void* stream) {
 extern "C" int b200nufft_dotc(const b200_c64* a, const b200_c64* b, int64_t n, double* out, void* stream) {
     ARG_CHECK(a && b && out && n >= 0, "dotc: bad arguments");
     ON_DEVICE(device_of(a));
+    const long long n4 = aligned16(a) && aligned16(b) ? n / 2 : 0;
     k_dotc<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(reinterpret_cast<const float2*>(a),
-                                                               reinterpret_cast<const float2*>(b), n, out);
+                                                               reinterpret_cast<const float2*>(b), n, n4, out);
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -271,7 +349,7 @@ extern "C" int b200nufft_cg_init(const b200_c64* b, const b200_c64* Ax, b200_c64
     ON_DEVICE(device_of(b));
     k_cg_init<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
         reinterpret_cast<const float2*>(b), reinterpret_cast<const float2*>(Ax), reinterpret_cast<float2*>(r),
-        reinterpret_cast<float2*>(p), rsold, n);
+        reinterpret_cast<float2*>(p), rsold, n, aligned16(b) && aligned16(Ax) && aligned16(r) && aligned16(p) ? n / 2 : 0);
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -283,7 +361,8 @@ extern "C" int b200nufft_cg_update_xr(b200_c64* x, b200_c64* r, const b200_c64* 
     ON_DEVICE(device_of(x));
     k_cg_update_xr<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
         reinterpret_cast<float2*>(x), reinterpret_cast<float2*>(r), reinterpret_cast<const float2*>(p),
-        reinterpret_cast<const float2*>(Ap), rsold, pAp, rsnew, n);
+        reinterpret_cast<const float2*>(Ap), rsold, pAp, rsnew, n,
+        aligned16(x) && aligned16(r) && aligned16(p) && aligned16(Ap) ? n / 2 : 0);
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -293,7 +372,8 @@ extern "C" int b200nufft_cg_update_p(b200_c64* p, const b200_c64* r, const doubl
     ARG_CHECK(p && r && rsnew && rsold && n >= 0, "cg_update_p: bad arguments");
     ON_DEVICE(device_of(p));
     k_cg_update_p<<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(
-        reinterpret_cast<float2*>(p), reinterpret_cast<const float2*>(r), rsnew, rsold, n);
+        reinterpret_cast<float2*>(p), reinterpret_cast<const float2*>(r), rsnew, rsold, n,
+        aligned16(p) && aligned16(r) ? n / 2 : 0);
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -323,10 +403,12 @@ extern "C" int b200nufft_axpby(b200_c64* out, double a_re, double a_im, const b2
     const float2 a = make_float2((float)a_re, (float)a_im), b = make_float2((float)b_re, (float)b_im);
     float2* o = reinterpret_cast<float2*>(out);
     const float2* xv = reinterpret_cast<const float2*>(x);
-    if (y && (b_re != 0.0 || b_im != 0.0))
-        k_axpby<true><<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(o, a, xv, b, reinterpret_cast<const float2*>(y), n);
+    const bool has_y = y && (b_re != 0.0 || b_im != 0.0);
+    const long long n4 = aligned16(out) && aligned16(x) && (!has_y || aligned16(y)) ? n / 2 : 0;
+    if (has_y)
+        k_axpby<true><<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(o, a, xv, b, reinterpret_cast<const float2*>(y), n, n4);
     else
-        k_axpby<false><<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(o, a, xv, b, nullptr, n);
+        k_axpby<false><<<stream_blocks(n), RED_TB, 0, as_stream(stream)>>>(o, a, xv, b, nullptr, n, n4);
     LAUNCH_CHECK();
     return B200_OK;
 }

@@ -645,3 +645,57 @@ def test_dense_cluster_splits_work_items(dev, geom):
     y = (rng.standard_normal(yshape) + 1j * rng.standard_normal(yshape)).astype(numpy.complex64)
     assert rel(A.forward(x), O.forward(x)) < TOL
     assert rel(A.adjoint(y), O.adjoint(y)) < TOL
+
+
+# ------------------------------------------------------------------------------ solver vector kernels
+@pytest.mark.parametrize('n', [1, 7, 1000, 2 * 148 * 4 * 256 * 4 + 3, 1_500_001])
+@pytest.mark.parametrize('misalign', [0, 1])
+def test_solver_vector_kernels(dev, n, misalign):
+    """b200nufft_dotc / axpby / cg_init / cg_update_xr / cg_update_p on odd lengths and on 8-byte-aligned-only vectors
+    (the kernels stream 16-byte pieces when they can and single elements otherwise) against float64 torch."""
+    from pynufft_b200 import solve as S, _lib
+    L = _lib.load()
+    g = torch.Generator(device='cpu').manual_seed(n + misalign)
+    def vec():
+        t = torch.view_as_complex(torch.randn((n + 1, 2), generator=g)).to(dev)
+        return t[misalign:misalign + n]          # misalign = 1: 8-byte aligned only
+    ops = S.CudaKrylovOps(L, dev)
+    x, y = vec(), vec()
+    xd, yd = x.to(torch.complex128), y.to(torch.complex128)
+    ref = complex(torch.vdot(xd, yd).item())
+    got = ops.dot(x, y)
+    assert abs(got - ref) <= 2e-6 * float(xd.abs().sum().item() ** 0.5 * yd.abs().sum().item() ** 0.5 + 1)
+    a, b = 0.3 - 1.1j, -0.7 + 0.2j
+    out = torch.empty_like(x)
+    ops.axpby(out, a, x, b, y)
+    assert float((out.to(torch.complex128) - (a * xd + b * yd)).abs().max()) < 1e-5
+    ops.axpby(out, a, x)
+    assert float((out.to(torch.complex128) - a * xd).abs().max()) < 1e-5
+    z = x.clone()
+    ops.axpby(z, a, z, 1.0, y)                   # in place
+    assert float((z.to(torch.complex128) - (a * xd + yd)).abs().max()) < 1e-5
+    # the CG kernels
+    cg = S.CudaVectorOps(L)
+    sc = cg.scalars(dev)
+    rs, pAp, rsn = sc[0:2], sc[2:4], sc[4:6]
+    bb, Ax = vec(), vec()
+    r, p = torch.empty_like(bb), torch.empty_like(bb)
+    cg.cg_init(bb, Ax, r, p, rs)
+    rd = bb.to(torch.complex128) - Ax.to(torch.complex128)
+    assert float((r.to(torch.complex128) - rd).abs().max()) < 1e-5 and torch.equal(r, p)
+    rs_ref = float((rd.abs() ** 2).sum().item())
+    assert abs(float(rs[0].item()) - rs_ref) <= 1e-5 * rs_ref + 1e-6
+    Ap = vec()
+    cg.dotc(p, Ap, pAp)
+    alpha = complex(rs[0].item(), rs[1].item()) / complex(pAp[0].item(), pAp[1].item())
+    xx = vec()
+    xref = xx.to(torch.complex128) + alpha * p.to(torch.complex128)
+    rref = r.to(torch.complex128) - alpha * Ap.to(torch.complex128)
+    cg.update_xr(xx, r, p, Ap, rs, pAp, rsn)
+    scale = 1.0 + abs(alpha)
+    assert float((xx.to(torch.complex128) - xref).abs().max()) < 1e-5 * scale
+    assert float((r.to(torch.complex128) - rref).abs().max()) < 1e-5 * scale
+    beta = complex(rsn[0].item(), rsn[1].item()) / complex(rs[0].item(), rs[1].item())
+    pref = r.to(torch.complex128) + beta * p.to(torch.complex128)
+    cg.update_p(p, r, rsn, rs)
+    assert float((p.to(torch.complex128) - pref).abs().max()) < 1e-5 * (1.0 + abs(beta)) * float(pref.abs().max() + 1)

@@ -65,6 +65,7 @@ x = A.to_device(rnd((128,) * 3))
 for _ in range(2):
     y = A._forward_device(x)
     xa = A._adjoint_device(y)
+pynufft_b200.solve.solve(A, y, 'bicgstab', maxiter=1)     # Krylov family on device vectors: k_axpby, k_dotc
 A.set_variant(3, 0)                      # column-sweep gather (not the default)
 y = A._forward_device(x)
 A.set_variant(0, 0)

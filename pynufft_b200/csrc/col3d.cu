@@ -129,11 +129,25 @@ __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M
     const long long T = gridDim.x * (long long)blockDim.x;
     for (long long j = i; j < nb; j += T) counters[j] = 0;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long j = i; j < n4; j += T) grid4[j] = z;
-    for (long long s = i; s < M; s += T) {
-        const float4 h = __ldg(side + s);               // P''.re, P''.im, original index
+    // the two dependent loads of a thread's first sample (side -> y[perm]) are issued around the first half of its
+    // zero-fill stores, so that the store stream covers their latency
+    const bool first = i < M;
+    float4 h = z;
+    if (first) h = __ldg(side + i);                     // P''.re, P''.im, original index
+    const long long half = (n4 / T / 2) * T;
+    for (long long j = i; j < half; j += T) grid4[j] = z;
+    float2 y0 = make_float2(0.f, 0.f);
+    if (first) y0 = y[(long long)__float_as_int(h.z) * nb];
+    for (long long j = half + i; j < n4; j += T) grid4[j] = z;
+    if (first) {
         const int m = __float_as_int(h.z);
-        for (int c = 0; c < nb; ++c) ys[(long long)c * Mpad + s] = cmulc(make_float2(h.x, h.y), y[(long long)m * nb + c]);
+        ys[i] = cmulc(make_float2(h.x, h.y), y0);
+        for (int c = 1; c < nb; ++c) ys[(long long)c * Mpad + i] = cmulc(make_float2(h.x, h.y), y[(long long)m * nb + c]);
+    }
+    for (long long s = i + T; s < M; s += T) {
+        const float4 hh = __ldg(side + s);
+        const int m = __float_as_int(hh.z);
+        for (int c = 0; c < nb; ++c) ys[(long long)c * Mpad + s] = cmulc(make_float2(hh.x, hh.y), y[(long long)m * nb + c]);
     }
 }
 

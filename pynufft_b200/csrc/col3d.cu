@@ -55,10 +55,11 @@ constexpr int IRING = COL_IRING;                      // gather: planes in the r
 static_assert(IRING == 8 || IRING == 10, "phase list below");
 constexpr int PBUF_PITCH = 33;                        // gather: partial sums pbuf[sample][lane], float2
 constexpr int PBUF_BYTES = CCH * PBUF_PITCH * 8;      // 4224
-constexpr int IWARP_BYTES = 8448;                     // gather: 2 * REC + PBUF + mbar, rounded to 128
+constexpr int SIDE_BYTES = CCH * 16;                   // gather: (P'', original index) of the chunk's samples
+constexpr int IWARP_BYTES = 8960;                     // gather: 2 * REC + PBUF + 2 * SIDE + mbar, rounded to 128
 static_assert(CT1 == 4 && CT2 == 5 && CRECW == 32 && CROWS == 3 * CNR, "record layout below assumes 4 x 5 columns");
 static_assert(2 * REC_BYTES + 2 * YS_BYTES + 128 + 16 <= GWARP_BYTES, "per-warp shared memory (scatter)");
-static_assert(2 * REC_BYTES + PBUF_BYTES + 16 <= IWARP_BYTES, "per-warp shared memory (gather)");
+static_assert(2 * REC_BYTES + PBUF_BYTES + 2 * SIDE_BYTES + 16 <= IWARP_BYTES && IWARP_BYTES % 128 == 0, "per-warp shared memory (gather)");
 
 // record words: [c1g[0..11] | c0[0..5] | p0 | run | w10[0..9] | 0 0]   (plan.cu k_col_records)
 
@@ -391,7 +392,8 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* ws = smem_raw + warp * IWARP_BYTES;
     P2* pbuf = reinterpret_cast<P2*>(ws + 2 * REC_BYTES);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + PBUF_BYTES);
+    unsigned char* sbuf = ws + 2 * REC_BYTES + PBUF_BYTES;              // [buffer] side entries of the chunk
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + PBUF_BYTES + 2 * SIDE_BYTES);
     const int c = blockIdx.y;
     const float2* gc = grid + (long long)c * g.Kprod;
     // lanes 30, 31 shadow lane 29's cells (finite values) with the always-zero record word 30 as their column weight:
@@ -428,8 +430,9 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
             const int s = wi.begin + k * CCH;
             const int ns = min(CCH, wi.end - s);
             const unsigned b = (gk + k) & 1;
-            mbar_expect(&mbar[b], (unsigned)(ns * CRECW * 4));
+            mbar_expect(&mbar[b], (unsigned)(ns * CRECW * 4) + (unsigned)(ns * 16));
             tma_bulk(ws + b * REC_BYTES, rec + (long long)s * CRECW, (unsigned)(ns * CRECW * 4), &mbar[b]);
+            tma_bulk(sbuf + b * SIDE_BYTES, side + s, (unsigned)(ns * 16), &mbar[b]);
         };
         fence_proxy_async();
         __syncwarp();
@@ -533,10 +536,11 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
                     if (lane == 0) issue(kc + 1);
                 }
                 ns = min(CCH, wi.end - s0);
-                // phase and original index of sample `lane` of the chunk (used after the reduction)
-                if (lane < ns) sd = __ldg(side + s0 + lane);
                 mbar_wait(&mbar[b], ((gk + kc) >> 1) & 1);
                 Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
+                // phase and original index of sample `lane` of the chunk (used after the reduction): they come with the
+                // records -- a global load here kept the long scoreboard busy across the chunk boundary
+                if (lane < ns) sd = reinterpret_cast<const float4*>(sbuf + b * SIDE_BYTES)[lane];
                 u = 0;
                 ++kc;
             }

@@ -46,6 +46,10 @@ if A._kspace_modulated():
     out['interp_mod_us'] = timed(lambda: lib.b200nufft_interp_modulated(A._plan, P(km.data_ptr()), P(yv.data_ptr()), 1, st()))
     out['gridding_mod_us'] = timed(lambda: lib.b200nufft_gridding_modulated(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()))
     out['pad_fft_mod_us'] = timed(lambda: lib.b200nufft_pad_fft_modulated(A._plan, P(x.data_ptr()), P(km.data_ptr()), 1, 1, 0, None, st()))
+    A.set_variant(3, 0)                 # column-sweep gather on the modulated grid
+    out['interp_col_us'] = timed(lambda: lib.b200nufft_interp_modulated(A._plan, P(km.data_ptr()), P(yv.data_ptr()), 1, st()))
+    out['interp_col_vs_generic'] = float(torch.linalg.norm(yv - y_gen) / torch.linalg.norm(y_gen))
+    out['pair_col_us'] = timed(lambda: A._adjoint_device(A._forward_device(x)))
     A.set_variant(2, 2)
     out['interp_tiled_us'] = timed(lambda: lib.b200nufft_interp(A._plan, P(k.data_ptr()), P(yv.data_ptr()), 1, st()))
     out['gridding_tiled_us'] = timed(lambda: lib.b200nufft_gridding(A._plan, P(y_gen.data_ptr()), P(grid.data_ptr()), 1, st()))

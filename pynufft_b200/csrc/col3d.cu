@@ -56,10 +56,14 @@ static_assert(IRING == 8 || IRING == 10, "phase list below");
 constexpr int PBUF_PITCH = 33;                        // gather: partial sums pbuf[sample][lane], float2
 constexpr int PBUF_BYTES = CCH * PBUF_PITCH * 8;      // 4224
 constexpr int SIDE_BYTES = CCH * 16;                   // gather: (P'', original index) of the chunk's samples
-constexpr int IWARP_BYTES = 8960;                     // gather: 2 * REC + PBUF + 2 * SIDE + mbar, rounded to 128
+#ifndef COL_I_NBUF
+#define COL_I_NBUF 2
+#endif
+constexpr int INB = COL_I_NBUF;                       // gather: record chunks in flight + the one in use
+constexpr int IWARP_BYTES = (INB * (REC_BYTES + SIDE_BYTES) + PBUF_BYTES + 8 * INB + 127) / 128 * 128;   // per warp
 static_assert(CT1 == 4 && CT2 == 5 && CRECW == 32 && CROWS == 3 * CNR, "record layout below assumes 4 x 5 columns");
 static_assert(2 * REC_BYTES + 2 * YS_BYTES + 128 + 16 <= GWARP_BYTES, "per-warp shared memory (scatter)");
-static_assert(2 * REC_BYTES + PBUF_BYTES + 2 * SIDE_BYTES + 16 <= IWARP_BYTES && IWARP_BYTES % 128 == 0, "per-warp shared memory (gather)");
+static_assert(INB >= 2 && INB <= 4 && IWARP_BYTES % 128 == 0, "per-warp shared memory (gather)");
 
 // record words: [c1g[0..11] | c0[0..5] | p0 | run | w10[0..9] | 0 0]   (plan.cu k_col_records)
 
@@ -391,9 +395,9 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* ws = smem_raw + warp * IWARP_BYTES;
-    P2* pbuf = reinterpret_cast<P2*>(ws + 2 * REC_BYTES);
-    unsigned char* sbuf = ws + 2 * REC_BYTES + PBUF_BYTES;              // [buffer] side entries of the chunk
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + PBUF_BYTES + 2 * SIDE_BYTES);
+    P2* pbuf = reinterpret_cast<P2*>(ws + INB * REC_BYTES);
+    unsigned char* sbuf = ws + INB * REC_BYTES + PBUF_BYTES;            // [buffer] side entries of the chunk
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + INB * (REC_BYTES + SIDE_BYTES) + PBUF_BYTES);
     const int c = blockIdx.y;
     const float2* gc = grid + (long long)c * g.Kprod;
     // lanes 30, 31 shadow lane 29's cells (finite values) with the always-zero record word 30 as their column weight:
@@ -404,8 +408,7 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
     const int lw = active ? lc : CCOLS;
     const int KK = g.K1 * g.K2;
     if (lane == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        for (int b = 0; b < INB; ++b) mbar_init(&mbar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncwarp();
@@ -429,14 +432,15 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
         auto issue = [&](int k) {      // lane 0 only
             const int s = wi.begin + k * CCH;
             const int ns = min(CCH, wi.end - s);
-            const unsigned b = (gk + k) & 1;
+            const unsigned b = (gk + k) % INB;
             mbar_expect(&mbar[b], (unsigned)(ns * CRECW * 4) + (unsigned)(ns * 16));
             tma_bulk(ws + b * REC_BYTES, rec + (long long)s * CRECW, (unsigned)(ns * CRECW * 4), &mbar[b]);
             tma_bulk(sbuf + b * SIDE_BYTES, side + s, (unsigned)(ns * 16), &mbar[b]);
         };
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) issue(0);
+        if (lane == 0)
+            for (int k = 0; k < INB - 1 && k < nchunks; ++k) issue(k);   // INB - 1 chunks ahead
 
         P2 G[IRING][CNR];              // register ring [plane mod IRING][row]: window planes p .. p+5, the rest in flight
 #pragma unroll
@@ -529,14 +533,14 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
         for (;;) {                      // chunks
             {
                 s0 = wi.begin + kc * CCH;
-                const unsigned b = (gk + kc) & 1;
-                if (kc + 1 < nchunks) {
+                const unsigned b = (gk + kc) % INB;
+                if (kc + INB - 1 < nchunks) {   // into the buffer of the chunk that was consumed last
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) issue(kc + 1);
+                    if (lane == 0) issue(kc + INB - 1);
                 }
                 ns = min(CCH, wi.end - s0);
-                mbar_wait(&mbar[b], ((gk + kc) >> 1) & 1);
+                mbar_wait(&mbar[b], ((gk + kc) / INB) & 1);
                 Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
                 // phase and original index of sample `lane` of the chunk (used after the reduction): they come with the
                 // records -- a global load here kept the long scoreboard busy across the chunk boundary

@@ -229,6 +229,11 @@ int b200nufft_gridding_is_modulated(b200nufft_plan_t plan);
  * gather reading the modulated grid directly) and ifft_crop_modulated all agree on that form; saves one pass over the
  * grid per application of G = interp^H interp.                                                                 */
 int b200nufft_kspace_modulated(b200nufft_plan_t plan);
+/* The same question for a call with nb coils.  2-D Jd = 6^2 plans keep the grid modulated, G'[g] = G[g] m0[g0] m1[g1], only on
+ * the batch-innermost path (even nb >= 8, power-of-two Kd): there the dim-0 FFT passes (csrc/fftbi.cu) apply / undo the
+ * modulation and the row-sweep kernels (csrc/sweep2d.cu) skip it; with any other nb the *_modulated entries of a 2-D plan
+ * work on the true grid. */
+int b200nufft_kspace_modulated_nb(b200nufft_plan_t plan, int nb);
 int b200nufft_interp_modulated(b200nufft_plan_t plan, const b200_c64* grid, b200_c64* y, int nb, void* stream);
 int b200nufft_gridding_modulated(b200nufft_plan_t plan, const b200_c64* y, b200_c64* grid, int nb, void* stream);
 int b200nufft_ifft_crop_modulated(b200nufft_plan_t plan, b200_c64* grid, b200_c64* x, int nb, int mode, int combine,

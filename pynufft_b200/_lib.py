@@ -58,6 +58,7 @@ SIGNATURES = {
     'b200nufft_plan_get_col_perm': (_i, [_vp, _vp, _vp, _vp]),
     'b200nufft_gridding_is_modulated': (_i, [_vp]),
     'b200nufft_kspace_modulated': (_i, [_vp]),
+    'b200nufft_kspace_modulated_nb': (_i, [_vp, _i]),
     'b200nufft_interp_modulated': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_gridding_modulated': (_i, [_vp, _vp, _vp, _i, _vp]),
     'b200nufft_ifft_crop_modulated': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -4,6 +4,7 @@
 #include <cufft.h>
 #include <stdint.h>
 #include <atomic>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -231,6 +232,13 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 static inline bool use_bi(const b200nufft_plan_s* p, int nb) {
     return p->has_sw2 && p->interp_variant != 1 && p->gridding_variant != 1 && nb >= 8 && (nb & 1) == 0;
 }
+// batch-innermost 2-D path with the fused FFT passes: the grid between the FFT and the sweep kernels is kept phase-
+// modulated inside forward / adjoint (the passes along dim 0 apply / undo the modulation; the kernels skip it)
+bool fftbi_supported(const Geom& g);
+static inline bool bi_fused_mod(const b200nufft_plan_s* p, int nb) {
+    static const bool off = [] { const char* e = getenv("B200NUFFT_BI_NOMOD"); return e && atoi(e) != 0; }();
+    return !off && use_bi(p, nb) && p->fft_variant != 1 && p->d_mod && fftbi_supported(p->g);
+}
 
 // tiled kernels (interp_tiled.cu / grid_tiled.cu); return B200_ERR_UNSUPPORTED if geometry does not fit
 // modulated: `grid` is the phase-modulated grid of the column-sweep gridding kernel (needs the plan's tables)
@@ -277,8 +285,8 @@ int single2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, c
 int single2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st);
 // sweep2d.cu: 2-D multi-coil kernels with the coil on the lanes, register-resident row sweep, batch-innermost grids
 bool sweep2d_supported(const Geom& g);
-int sweep2d_interp(b200nufft_plan_t p, const float2* grid_bi, float2* y, int nb, cudaStream_t st);
-int sweep2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_bi, int nb, cudaStream_t st);   // zero-fills
+int sweep2d_interp(b200nufft_plan_t p, const float2* grid_bi, float2* y, int nb, cudaStream_t st, bool modulated = false);
+int sweep2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_bi, int nb, cudaStream_t st, bool modulated = false);   // zero-fills
 int sweep2d_scale_pad(b200nufft_plan_t p, const float2* x, float2* grid_bi, int nb, int apply_sn, int x_single,
                       const float2* sens, cudaStream_t st);
 int sweep2d_crop_scale(b200nufft_plan_t p, const float2* grid_bi, float2* x, int nb, int mode, int combine,
@@ -289,8 +297,9 @@ int sweep2d_pad_fft(b200nufft_plan_t p, const float2* x, float2* grid_bi, int nb
 // fftbi.cu: fused, pruned FFT passes on batch-innermost grids (power-of-two Kd, 64 .. 1024)
 bool fftbi_supported(const Geom& g);
 int fftbi_forward(b200nufft_plan_t p, const float2* x, float2* grid_bi, int nb, int apply_sn, int x_single,
-                  const float2* sens, cudaStream_t st);
-int fftbi_inverse(b200nufft_plan_t p, float2* grid_bi, float2* x, int nb, int mode, float scale, cudaStream_t st);
+                  const float2* sens, cudaStream_t st, bool modulate = false);
+int fftbi_inverse(b200nufft_plan_t p, float2* grid_bi, float2* x, int nb, int mode, float scale, cudaStream_t st,
+                  bool demodulate = false);
 int sweep2d_ifft_to_scratch(b200nufft_plan_t p, const float2* grid_bi, int nb, cudaStream_t st);   // coil-major result in p->d_grid2
 
 

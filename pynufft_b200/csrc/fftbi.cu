@@ -94,6 +94,10 @@ struct BiPass {
     const float2* sens;     // coil maps (image layout) or NULL
     int x_single, apply_sn; // as scale_pad / crop_scale (apply_sn: 0 none, 1 multiply, 2 divide)
     float scale;
+    // mode 0 along dim 0 only: phase modulation of the grid (sweep2d.cu works on G[g] m0[g0] m1[g1]): the forward pass
+    // multiplies its outputs by mod_t[f] * mod_l[line], the inverse pass its inputs by the conjugate
+    const float2* mod_t;    // m0, indexed by the position along the transform; NULL = none
+    const float2* mod_l;    // m1, indexed by the line
 };
 
 // one in-place DIF stage: radix R on sub-transforms of length L inside a line of N points (all compile-time)
@@ -197,6 +201,10 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
             if (i < a.nin && cact) cp_async8(d, src + i * es);
             else *d = make_float2(0.f, 0.f);
         }
+        if (a.mode == 0 && a.mod_t) {                       // aux[i] = m_t[i] m_l[line]
+            const float2 ml = __ldg(a.mod_l + line);
+            for (int i = t; i < N; i += FTB) aux[i] = cmul(__ldg(a.mod_t + i), ml);
+        }
         if (a.mode == 2) {                                  // fsv[f] = scale * (sn | 1 / sn) of image column f
             const float s0 = a.sn_other[line];
             for (int f = t; f < a.nout; f += FTB) {
@@ -208,6 +216,13 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
             }
         }
         cp_async_wait_all();
+        if (DIR > 0 && a.mode == 0 && a.mod_t) {            // inverse: the scatter left the grid modulated
+            __syncthreads();
+            for (int i = gi; i < a.nin; i += FTB / NCO) {
+                float2* d = buf + i * NCO + c;
+                *d = cmulc(aux[i], *d);
+            }
+        }
     }
     __syncthreads();
     stages<DIR, LOGN>(buf, tw, c, gi);
@@ -227,9 +242,10 @@ __global__ void __launch_bounds__(FTB) k_fftbi(BiPass a) {
         float2* dst = a.out + (long long)line * a.lstride * a.nb + cb + c;
         const long long es = a.estride * a.nb;
 #pragma unroll 8
+        const bool modout = DIR < 0 && a.mod_t;             // forward: the gather reads the modulated grid
         for (int pos = gi; pos < N; pos += FTB / NCO) {
             const int f = rv[pos];
-            if (f < a.nout && cact) dst[f * es] = buf[pos * NCO + c];
+            if (f < a.nout && cact) dst[f * es] = modout ? cmul(buf[pos * NCO + c], aux[f]) : buf[pos * NCO + c];
         }
     }
 }
@@ -332,8 +348,9 @@ static int launch(const BiPass& a, int nlines, int nb, cudaStream_t st) {
 }
 
 // grid_bi <- FFT2(zero-pad(x * [sn] * [sens]))
+// modulate: the grid is written as G[g] m0[g0] m1[g1] (what sweep2d_interp(..., modulated) reads)
 int fftbi_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, int apply_sn, int x_single,
-                  const float2* sens, cudaStream_t st) {
+                  const float2* sens, cudaStream_t st, bool modulate) {
     int rc = ensure_tables(p);
     if (rc) return rc;
     const Geom& g = p->g;
@@ -356,11 +373,17 @@ int fftbi_forward(b200nufft_plan_t p, const float2* x, float2* grid, int nb, int
     b.out = grid;
     b.nin = g.N[0];
     b.nout = g.K[0];
+    if (modulate) {
+        b.mod_t = p->d_mod;
+        b.mod_l = p->d_mod + g.K[0];
+    }
     return launch<-1>(b, g.K[1], nb, st);
 }
 
 // x <- crop(IFFT2(grid_bi)) * f * scale (image layout, all coils); the grid is overwritten (partially transformed)
-int fftbi_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode, float scale, cudaStream_t st) {
+// demodulate: the grid is G[g] m0[g0] m1[g1] (left so by sweep2d_gridding(..., modulated))
+int fftbi_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode, float scale, cudaStream_t st,
+                  bool demodulate) {
     int rc = ensure_tables(p);
     if (rc) return rc;
     const Geom& g = p->g;
@@ -369,6 +392,10 @@ int fftbi_inverse(b200nufft_plan_t p, float2* grid, float2* x, int nb, int mode,
     a.out = grid;
     a.nin = g.K[0];
     a.nout = g.N[0];
+    if (demodulate) {
+        a.mod_t = p->d_mod;
+        a.mod_l = p->d_mod + g.K[0];
+    }
     rc = launch<1>(a, g.K[1], nb, st);
     if (rc) return rc;
     BiPass b = base_pass(p, 1, nb);             // B': along dim 1 on the N0 rows, cropped + scaled into the image

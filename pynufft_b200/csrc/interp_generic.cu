@@ -103,6 +103,7 @@ k_gridding_generic(Geom g, const float* __restrict__ rec, long long M, const flo
 
 int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool grid_modulated) {
     if (p->M == 0) return B200_OK;
+    if (grid_modulated && bi_fused_mod(p, nb)) return sweep2d_interp(p, grid, y, nb, st, true);   // 2-D multi-coil
     if (grid_modulated) {
         if (!interp_takes_modulated(p)) {
             b200_set_error("interp: this plan / variant cannot read a phase-modulated grid");
@@ -140,7 +141,8 @@ int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cud
         if (rc || modulated_ok) return rc;
         return col3d_demodulate(p, grid, nb, st);
     }
-    if (p->M > 0 && use_bi(p, nb)) return sweep2d_gridding(p, y, grid, nb, st);   // batch-innermost grid, zero-fills
+    if (p->M > 0 && use_bi(p, nb))               // batch-innermost grid, zero-fills; modulated when the caller takes it so
+        return sweep2d_gridding(p, y, grid, nb, st, modulated_ok && bi_fused_mod(p, nb));
     CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
     if (p->M == 0) return B200_OK;
     if (p->gridding_variant != 1 && single2d_supported(p->g)) return single2d_gridding(p, y, grid, nb, st);
@@ -171,6 +173,12 @@ extern "C" int b200nufft_interp_modulated(b200nufft_plan_t p, const b200_c64* gr
 // 1 if interp_modulated / gridding_modulated / ifft_crop_modulated all work on the phase-modulated grid
 extern "C" int b200nufft_kspace_modulated(b200nufft_plan_t p) {
     return (p && gridding_modulated(p) && interp_takes_modulated(p)) ? 1 : 0;
+}
+// the same for a call with nb coils: 2-D plans keep the grid modulated only on the batch-innermost path (even nb >= 8)
+extern "C" int b200nufft_kspace_modulated_nb(b200nufft_plan_t p, int nb) {
+    if (!p || nb < 1) return 0;
+    if (p->M > 0 && bi_fused_mod(p, nb)) return 1;
+    return (!use_bi(p, nb) && gridding_modulated(p) && interp_takes_modulated(p)) ? 1 : 0;
 }
 
 extern "C" int b200nufft_gridding(b200nufft_plan_t p, const b200_c64* y, b200_c64* grid, int nb, void* stream) {

@@ -327,7 +327,8 @@ static int pad_fft_impl(b200nufft_plan_t p, const b200_c64* x, b200_c64* grid, i
                               x_single, reinterpret_cast<const float2*>(sens), modulated, as_stream(stream));
     if (use_bi(p, nb) && p->fft_variant != 1 && fftbi_supported(p->g))     // fused pruned passes on the layout itself
         return fftbi_forward(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
-                             x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
+                             x_single, reinterpret_cast<const float2*>(sens), as_stream(stream),
+                             modulated && bi_fused_mod(p, nb));
     if (use_bi(p, nb))              // batch-innermost grid out: coil-major pad + cuFFT on a scratch, one transposing pass
         return sweep2d_pad_fft(p, reinterpret_cast<const float2*>(x), reinterpret_cast<float2*>(grid), nb, apply_sn,
                                x_single, reinterpret_cast<const float2*>(sens), as_stream(stream));
@@ -359,6 +360,7 @@ static int ifft_crop_impl(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int n
     cudaStream_t st = as_stream(stream);
     const float scale = 1.0f / (float)p->g.Kprod;
     const bool mod = modulated && gridding_modulated(p);
+    const bool bi_mod = modulated && p->M > 0 && bi_fused_mod(p, nb);    // 2-D multi-coil: as sweep2d_gridding(..., modulated) left it
     if (p->fft_variant != 1 && fft256_supported(p->g)) {
         if (!combine)
             return fft256_inverse(p, reinterpret_cast<float2*>(grid), reinterpret_cast<float2*>(x), nb, mode, scale,
@@ -376,13 +378,13 @@ static int ifft_crop_impl(b200nufft_plan_t p, b200_c64* grid, b200_c64* x, int n
     int rc = B200_OK;
     if (use_bi(p, nb) && p->fft_variant != 1 && fftbi_supported(p->g)) {
         if (!combine)
-            return fftbi_inverse(p, reinterpret_cast<float2*>(grid), reinterpret_cast<float2*>(x), nb, mode, scale, st);
+            return fftbi_inverse(p, reinterpret_cast<float2*>(grid), reinterpret_cast<float2*>(x), nb, mode, scale, st, bi_mod);
         if (p->xc_nb < nb) {
             if (p->d_xc) { CUDA_TRY(cudaFree(p->d_xc)); p->d_xc = nullptr; p->xc_nb = 0; }
             CUDA_TRY(cudaMalloc(&p->d_xc, sizeof(float2) * p->g.Nprod * nb));
             p->xc_nb = nb;
         }
-        rc = fftbi_inverse(p, reinterpret_cast<float2*>(grid), p->d_xc, nb, mode, scale, st);
+        rc = fftbi_inverse(p, reinterpret_cast<float2*>(grid), p->d_xc, nb, mode, scale, st, bi_mod);
         if (rc) return rc;
         return combine_coils(p->d_xc, reinterpret_cast<const float2*>(sens), reinterpret_cast<float2*>(x), p->g.Nprod, nb,
                              st);
@@ -419,7 +421,8 @@ static int forward_impl(b200nufft_plan_t p, const float2* x, int x_single, const
     int rc = ensure_scratch(p, nb);
     if (rc) return rc;
     // the column-sweep gather reads the phase-modulated grid: the forward FFT passes produce it directly
-    const bool mod = interp_uses_col(p) && !use_bi(p, nb);
+    // (3-D); the 2-D multi-coil FFT pass along dim 0 writes the modulated grid the row-sweep gather reads
+    const bool mod = (interp_uses_col(p) && !use_bi(p, nb)) || bi_fused_mod(p, nb);
     rc = pad_fft_impl(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
                       x_single, reinterpret_cast<const b200_c64*>(sens), stream, mod);
     if (rc) return rc;

@@ -235,6 +235,9 @@ __global__ void k_sw2_scale_pad_cm(int N0, int N1, int K0, int K1, int sn0, int 
         X##P = *reinterpret_cast<const float2*>(R + 16);                                           \
     }
 
+// MODG: the grid is left phase-modulated (the inverse FFT pass along dim 0 undoes it, fftbi.cu); the flush is then a
+// plain RED of the accumulators and the per-row factor is never loaded
+template <bool MODG>
 __global__ void __launch_bounds__(SWARPS * 32, 4)
 k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const float* __restrict__ rec,
                const float2* __restrict__ mod, const float2* __restrict__ y, float2* __restrict__ grid) {
@@ -344,7 +347,7 @@ k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const f
 #define SW2_S_PHASE(KC)                                                                            \
     case KC: {                                                                                     \
         if (u == ns) { K = KC; goto chunk_done; }                                                  \
-        const float2 f0r = __ldg(m0 + pw);                 /* consumed at the flush below */       \
+        const float2 f0r = MODG ? make_float2(1.f, 0.f) : __ldg(m0 + pw);   /* consumed at the flush below */ \
         {                                                                                          \
             const int2 pr = *reinterpret_cast<const int2*>(Rb + u * RECW + 6);     /* p0, run */   \
             pnext = pr.x;                                                                          \
@@ -363,7 +366,7 @@ k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const f
             const float2 f0 = make_float2(f0r.x, -f0r.y);                                          \
             const long long rowoff = (long long)pw * g.K1 * nb;                                    \
             _Pragma("unroll") for (int i = 0; i < CH; ++i) {                                       \
-                const float2 v = cmul(A[KC][i], cmul(f0, m1c[i]));                                 \
+                const float2 v = MODG ? A[KC][i] : cmul(A[KC][i], cmul(f0, m1c[i]));               \
                 if (cact) red_v2(grid + rowoff + coff[i], v);                                      \
                 A[KC][i] = make_float2(0.f, 0.f);                                                  \
             }                                                                                      \
@@ -433,6 +436,9 @@ item_done:;
 // ---------------------------------------------------------------------------------------------------------
 // interpolation (gather): y = A k, true grid in, batch-innermost
 // ---------------------------------------------------------------------------------------------------------
+// MODG: the grid arrives phase-modulated (written so by the forward FFT pass along dim 0, fftbi.cu): rows enter the
+// window as they are
+template <bool MODG>
 __global__ void __launch_bounds__(SWARPS * 32, 4)
 k_sw2_interp(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const float* __restrict__ rec,
              const float2* __restrict__ mod, const float2* __restrict__ grid, float2* __restrict__ y) {
@@ -491,6 +497,7 @@ k_sw2_interp(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const flo
     };
     // the values of row `row` (landed): this lane's four columns times the modulation m0[row] m1[col]
     auto row_factor = [&](int row) {    // m0[row], issued well before it is needed
+        if (MODG) return make_float2(1.f, 0.f);
         int rw = row;
         if (rw >= g.K0) rw -= g.K0;
         return __ldg(m0 + rw);
@@ -498,7 +505,7 @@ k_sw2_interp(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const flo
     auto row_values = [&](int row, const float2 f0, float2 (&v)[CH]) {
         const float2* rp = ring + (row & (RS - 1)) * (CB * NCL) + (CH * lh) * NCL + lc;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = cmul(rp[i * NCL], cmul(f0, m1v[i]));
+        for (int i = 0; i < CH; ++i) v[i] = MODG ? rp[i * NCL] : cmul(rp[i * NCL], cmul(f0, m1v[i]));
         __syncwarp();                   // all lanes have read the slot before it is fetched into again
     };
     const int nchunks = (wi.end - wi.begin + CCH - 1) / CCH;
@@ -674,8 +681,10 @@ static Sw2Geom sw2_geom(const Geom& g, int nb) {
 
 static int sw2_attrs(b200nufft_plan_t p) {
     if (!p->attr_sw2) {
-        CUDA_TRY(cudaFuncSetAttribute(k_sw2_gridding, cudaFuncAttributeMaxDynamicSharedMemorySize, SWARPS * GW_PITCH));
-        CUDA_TRY(cudaFuncSetAttribute(k_sw2_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, SWARPS * IW_PITCH));
+        CUDA_TRY(cudaFuncSetAttribute(k_sw2_gridding<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWARPS * GW_PITCH));
+        CUDA_TRY(cudaFuncSetAttribute(k_sw2_gridding<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWARPS * GW_PITCH));
+        CUDA_TRY(cudaFuncSetAttribute(k_sw2_interp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWARPS * IW_PITCH));
+        CUDA_TRY(cudaFuncSetAttribute(k_sw2_interp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWARPS * IW_PITCH));
         p->attr_sw2 = true;
     }
     return B200_OK;
@@ -776,25 +785,35 @@ int sweep2d_ifft_to_scratch(b200nufft_plan_t p, const float2* grid, int nb, cuda
     return B200_OK;
 }
 
-int sweep2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st) {
+// modulated: the grid is G[g] m0[g0] m1[g1] (fftbi_forward(..., modulate) writes it so)
+int sweep2d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool modulated) {
     int rc = sw2_attrs(p);
     if (rc) return rc;
     if (p->n_sw_work == 0) return B200_OK;
     dim3 gr((unsigned)((p->n_sw_work + SWARPS - 1) / SWARPS), (unsigned)((nb + NCL - 1) / NCL));
-    k_sw2_interp<<<gr, SWARPS * 32, SWARPS * IW_PITCH, st>>>(sw2_geom(p->g, nb), p->d_sw_work, p->n_sw_work, p->d_sw_rec,
-                                                            p->d_mod, grid, y);
+    if (modulated)
+        k_sw2_interp<true><<<gr, SWARPS * 32, SWARPS * IW_PITCH, st>>>(sw2_geom(p->g, nb), p->d_sw_work, p->n_sw_work,
+                                                                      p->d_sw_rec, p->d_mod, grid, y);
+    else
+        k_sw2_interp<false><<<gr, SWARPS * 32, SWARPS * IW_PITCH, st>>>(sw2_geom(p->g, nb), p->d_sw_work, p->n_sw_work,
+                                                                       p->d_sw_rec, p->d_mod, grid, y);
     LAUNCH_CHECK();
     return B200_OK;
 }
 
-int sweep2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st) {
+// modulated: the grid is left as G[g] m0[g0] m1[g1] (fftbi_inverse(..., demodulate) takes it)
+int sweep2d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool modulated) {
     int rc = sw2_attrs(p);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));
     if (p->n_sw_work == 0) return B200_OK;
     dim3 gr((unsigned)((p->n_sw_work + SWARPS - 1) / SWARPS), (unsigned)((nb + NCL - 1) / NCL));
-    k_sw2_gridding<<<gr, SWARPS * 32, SWARPS * GW_PITCH, st>>>(sw2_geom(p->g, nb), p->d_sw_work, p->n_sw_work, p->d_sw_rec,
-                                                              p->d_mod, y, grid);
+    if (modulated)
+        k_sw2_gridding<true><<<gr, SWARPS * 32, SWARPS * GW_PITCH, st>>>(sw2_geom(p->g, nb), p->d_sw_work, p->n_sw_work,
+                                                                        p->d_sw_rec, p->d_mod, y, grid);
+    else
+        k_sw2_gridding<false><<<gr, SWARPS * 32, SWARPS * GW_PITCH, st>>>(sw2_geom(p->g, nb), p->d_sw_work, p->n_sw_work,
+                                                                         p->d_sw_rec, p->d_mod, y, grid);
     LAUNCH_CHECK();
     return B200_OK;
 }

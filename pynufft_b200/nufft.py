@@ -269,12 +269,13 @@ class NUFFT:
         _lib.check(fn(self._plan, _ptr(y), _ptr(store), nb, self._stream()))
         return view
 
-    def _kspace_modulated(self):
-        """True when gridding, interp and the inverse FFT passes can all work on the phase-modulated grid of the
-        column-sweep gridding kernel (csrc/col3d.cu): k-space solvers then iterate on modulated vectors
-        (G' = D G D^H with D diagonal and unitary has the same CG scalars) and skip one grid pass per G."""
+    def _kspace_modulated(self, nb=1):
+        """True when gridding, interp and the inverse FFT passes can all work on the phase-modulated grid of the sweep
+        kernels (csrc/col3d.cu; csrc/sweep2d.cu for 2-D calls with an even number >= 8 of coils): k-space solvers then
+        iterate on modulated vectors (G' = D G D^H with D diagonal and unitary has the same CG scalars) and skip the
+        modulation work per G."""
         self._require_plan()
-        return int(self._lib.b200nufft_kspace_modulated(self._plan)) == 1
+        return int(self._lib.b200nufft_kspace_modulated_nb(self._plan, int(nb))) == 1
 
     def _k2xx_device(self, k):
         """Inverse FFT (in place on k when k is a coil-major view, like the reference's in-place FFT) + crop."""

@@ -93,7 +93,8 @@ def cg(nufft, gy, maxiter=30, group=None):
     if group is not None:
         import torch.distributed as dist
         allreduce = lambda t: dist.all_reduce(t, group=group)
-    mod = nufft._kspace_modulated()      # iterate on phase-modulated k-space vectors where the kernels allow it
+    nb_in = int(gy.shape[1]) if gy.dim() == 2 else 1
+    mod = nufft._kspace_modulated(nb_in)   # iterate on phase-modulated k-space vectors where the kernels allow it
     bview = nufft._y2k_device(gy, modulated=mod)
     batched = bview.dim() == nufft.ndims + 1
     nb = int(bview.shape[-1]) if batched else 1

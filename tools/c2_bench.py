@@ -25,10 +25,12 @@ out = {'M': om.shape[0], 'forward_one2many_us': timed(lambda: A.forward_one2many
        'adjoint_many2one_us': timed(lambda: A.adjoint_many2one(y)),
        'interp32_us': timed(lambda: A._k2y_device(k)), 'gridding32_us': timed(lambda: A._y2k_device(y))}
 import time
+A._solve_device(y, 'cg', maxiter=3)          # warm-up: scratch buffers, first launches
 torch.cuda.synchronize(); t0 = time.perf_counter(); A._solve_device(y, 'cg', maxiter=100); torch.cuda.synchronize()
 out['cg100_s'] = time.perf_counter() - t0
 A1 = pynufft_b200.NUFFT('cuda:0'); A1.plan(om, Nd, Kd, Jd)
 y1 = A1._forward_device(s)
+A1._solve_device(y1, 'L1TVOLS', maxiter=3, rho=2)
 torch.cuda.synchronize(); t0 = time.perf_counter(); A1._solve_device(y1, 'L1TVOLS', maxiter=100, rho=2); torch.cuda.synchronize()
 out['l1tvols100_s'] = time.perf_counter() - t0
 algo = 8 * B * 512 * 512 + 12 * om.shape[0] * 12 + 8 * B * om.shape[0]

@@ -28,6 +28,8 @@ for Nd, Kd, Jd, M, batch in (((15, 20, 24), (30, 50, 48), (6, 6, 6), 3000, None)
         A.solve(ys, 'cg', maxiter=2)
     if batch is None:
         A.solve(A.forward(x), 'cg', maxiter=2)
+        A.solve(A.forward(x), 'bicgstab', maxiter=2)        # k_axpby, k_dotc on odd lengths
+        A.solve(A.forward(x), 'lsmr', maxiter=2)
         xp = torch.from_numpy(x).pin_memory().numpy()
         A.forward(xp, out=torch.empty(M, dtype=torch.complex64).pin_memory().numpy(), slot=1); A.wait('forward', 1)
     A.release()

@@ -491,6 +491,9 @@ def run_ours(args, rank, world, local_rank):
         c2t = {}
         c2t['interp'] = timed(lambda: lib.b200nufft_interp(A2._plan, P(k2s.data_ptr()), P(y2.data_ptr()), 32, st()), 30, 3) / 30
         c2t['gridding'] = timed(lambda: lib.b200nufft_gridding(A2._plan, P(y2.data_ptr()), P(k2s.data_ptr()), 32, st()), 30, 3) / 30
+        if A2._kspace_modulated(32):    # the same two stages on the phase-modulated grid forward / adjoint / CG keep
+            c2t['interp_modulated_grid'] = timed(lambda: lib.b200nufft_interp_modulated(A2._plan, P(k2s.data_ptr()), P(y2.data_ptr()), 32, st()), 30, 3) / 30
+            c2t['gridding_modulated_grid'] = timed(lambda: lib.b200nufft_gridding_modulated(A2._plan, P(y2.data_ptr()), P(k2s.data_ptr()), 32, st()), 30, 3) / 30
         c2t['forward_one2many'] = timed(lambda: A2.forward_one2many(s2), 30, 3) / 30
         c2t['adjoint_many2one'] = timed(lambda: A2.adjoint_many2one(y2), 30, 3) / 30
         config2 = {'ms': c2t, 'algorithmic_bytes': algo2,

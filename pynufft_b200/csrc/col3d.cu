@@ -48,29 +48,39 @@ constexpr int CWARPS = 4;                 // warps per CTA (each warp works on i
 constexpr int REC_BYTES = CCH * CRECW * 4;            // 2048
 constexpr int YS_BYTES = 160;                         // up to 18 pre-gathered values (8 B) per chunk, 16-byte multiple
 constexpr int GWARP_BYTES = 4608;                     // scatter: 2 * REC + 2 * YS + dummy record + mbar, rounded to 128
-#ifndef COL_IRING
-#define COL_IRING 10
+#ifndef COL_I_CTAS
+#define COL_I_CTAS 6
 #endif
-constexpr int IRING = COL_IRING;                      // gather: planes in the register ring (window 6 + in flight)
-static_assert(IRING == 8 || IRING == 10, "phase list below");
-constexpr int PBUF_PITCH = 33;                        // gather: partial sums pbuf[sample][lane], float2
-constexpr int PBUF_BYTES = CCH * PBUF_PITCH * 8;      // 4224
+#ifndef COL_I_PRING
+#define COL_I_PRING 3
+#endif
+#ifndef COL_I_PB
+#define COL_I_PB 16
+#endif
+#ifndef COL_I_PAIR
+#define COL_I_PAIR 1
+#endif
+constexpr int PRING = COL_I_PRING;                    // gather: planes in flight ahead of the window (shared-memory ring)
+constexpr int PSLOT = 32 * CNR * 8;                   // gather: bytes per ring plane (3 cells per lane)
+constexpr int PB = COL_I_PB;                          // gather: samples per reduction group (transpose buffer rows)
+constexpr int PBUF_PITCH = 33;                        // gather: partial sums pbuf[sample mod PB][lane], float2
+constexpr int PBUF_BYTES = PB * PBUF_PITCH * 8;
 constexpr int SIDE_BYTES = CCH * 16;                   // gather: (P'', original index) of the chunk's samples
 #ifndef COL_I_NBUF
 #define COL_I_NBUF 2
 #endif
 constexpr int INB = COL_I_NBUF;                       // gather: record chunks in flight + the one in use
-constexpr int IWARP_BYTES = (INB * (REC_BYTES + SIDE_BYTES) + PBUF_BYTES + 8 * INB + 127) / 128 * 128;   // per warp
+constexpr int IWARP_BYTES = (INB * (REC_BYTES + SIDE_BYTES) + PBUF_BYTES + PRING * PSLOT + 8 * INB + 127) / 128 * 128;   // per warp
 static_assert(CT1 == 4 && CT2 == 5 && CRECW == 32 && CROWS == 3 * CNR, "record layout below assumes 4 x 5 columns");
 static_assert(2 * REC_BYTES + 2 * YS_BYTES + 128 + 16 <= GWARP_BYTES, "per-warp shared memory (scatter)");
-static_assert(INB >= 2 && INB <= 4 && IWARP_BYTES % 128 == 0, "per-warp shared memory (gather)");
+static_assert(INB >= 2 && INB <= 4 && IWARP_BYTES % 128 == 0 && PBUF_BYTES % 16 == 0, "per-warp shared memory (gather)");
+static_assert(PRING >= 1 && PRING <= 6 && (PB == 8 || PB == 16) && CCH % PB == 0 && (!COL_I_PAIR || PB == CCH), "gather ring / reduction groups");
 
 // record words: [c1g[0..11] | c0[0..5] | p0 | run | w10[0..9] | 0 0]   (plan.cu k_col_records)
 
 struct ColGeom {
     int K0, K1, K2, nq2;
     int dbg;                    // experiments (B200NUFFT_COL_DBG): bit 0 = skip the REDs / plane loads
-    int pf_ahead;               // gather: planes between the register ring's newest plane and the L2 prefetch (0 = none)
     long long Kprod;
 };
 
@@ -385,10 +395,27 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
 // ---------------------------------------------------------------------------------------------------------
 // interpolation (gather) on the phase-modulated grid
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 ldg_u64(const float2* p) { return __ldg(p); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
-__global__ void __launch_bounds__(CWARPS * 32, 4)
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ float2 lds64(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int mod6(int p) { p %= 6; return p < 0 ? p + 6 : p; }
+
+// The window planes p .. p+5 live in registers (slot = plane mod 6, static inside a phase); the planes behind it arrive
+// in a per-warp shared-memory ring by 8-byte cp.async copies, PRING planes ahead of the window, each lane fetching and
+// later reading back its OWN three cells (no cross-lane traffic, so the per-thread cp.async groups are all the
+// synchronisation there is).  The L2 / DRAM latency of a plane is covered by PRING plane advances instead of by
+// registers that hold loads in flight, which is what lets six CTAs of four warps share an SM.
+__global__ void __launch_bounds__(CWARPS * 32, COL_I_CTAS)
 k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __restrict__ counter,
              const float* __restrict__ rec, const float4* __restrict__ side, const float2* __restrict__ grid,
              float2* __restrict__ y, int nb) {
@@ -397,7 +424,8 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
     unsigned char* ws = smem_raw + warp * IWARP_BYTES;
     P2* pbuf = reinterpret_cast<P2*>(ws + INB * REC_BYTES);
     unsigned char* sbuf = ws + INB * REC_BYTES + PBUF_BYTES;            // [buffer] side entries of the chunk
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + INB * (REC_BYTES + SIDE_BYTES) + PBUF_BYTES);
+    const unsigned pring = smem_u32(ws + INB * (REC_BYTES + SIDE_BYTES) + PBUF_BYTES) + lane * 8;   // this lane's entry of ring plane 0, cell 0
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + INB * (REC_BYTES + SIDE_BYTES) + PBUF_BYTES + PRING * PSLOT);
     const int c = blockIdx.y;
     const float2* gc = grid + (long long)c * g.Kprod;
     // lanes 30, 31 shadow lane 29's cells (finite values) with the always-zero record word 30 as their column weight:
@@ -441,25 +469,50 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
         __syncwarp();
         if (lane == 0)
             for (int k = 0; k < INB - 1 && k < nchunks; ++k) issue(k);   // INB - 1 chunks ahead
+        cp_async_wait_all();           // plane copies of the previous item that ran past its last sample
 
-        P2 G[IRING][CNR];              // register ring [plane mod IRING][row]: window planes p .. p+5, the rest in flight
+        P2 G[6][CNR];                  // window planes p .. p+5: [plane mod 6][row]
 #pragma unroll
-        for (int s = 0; s < IRING; ++s)
+        for (int s = 0; s < 6; ++s)
 #pragma unroll
             for (int i = 0; i < CNR; ++i) G[s][i] = make_float2(0.f, 0.f);
         int kc = 0, u = 0, ns = 0, s0 = 0;
-        int K = 0, p = 0, pnext = 0;
+        int K = 0, p = 0, pnext = 0, nrun = 0;
         bool started = false;
         const float* Rb = nullptr;
-        float4 sd = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* Sb = nullptr;    // (P'', original index) entries of the chunk
+        // sum the rows of the transpose buffer (samples base .. base + PB - 1 of the chunk): lane -> (sample, part of its row)
+        auto reduce_group = [&](int base) {
+            __syncwarp();
+            constexpr int PARTS = 32 / PB, LEN = 32 / PARTS;      // PB = 8: 4 parts of 8 lanes' sums
+            const int su = lane & (PB - 1), h = lane / PB;
+            const P2* pb = pbuf + su * PBUF_PITCH + h * LEN;
+            float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int l = 0; l < LEN; ++l) {
+                const float2 v = pb[l];
+                sum.x += v.x;
+                sum.y += v.y;
+            }
+#pragma unroll
+            for (int o = 16; o >= PB; o >>= 1) {
+                sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+                sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+            }
+            if (lane < PB && base + lane < ns) {
+                const float4 sd = Sb[base + lane];
+                y[(long long)__float_as_int(sd.z) * nb + c] = cmul(make_float2(sd.x, sd.y), sum);
+            }
+            __syncwarp();
+        };
 
 #define COL_DOT_ROW(KC, I, C0a, C0b)                                        \
-    P2 e##I = fmul2(bc2(C0a.x), G[(KC + 0) % IRING][I]);                       \
-    ffma2_acc(e##I, bc2(C0a.y), G[(KC + 1) % IRING][I]);                        \
-    ffma2_acc(e##I, bc2(C0a.z), G[(KC + 2) % IRING][I]);                        \
-    ffma2_acc(e##I, bc2(C0a.w), G[(KC + 3) % IRING][I]);                        \
-    ffma2_acc(e##I, bc2(C0b.x), G[(KC + 4) % IRING][I]);                        \
-    ffma2_acc(e##I, bc2(C0b.y), G[(KC + 5) % IRING][I]);
+    P2 e##I = fmul2(bc2(C0a.x), G[(KC + 0) % 6][I]);                           \
+    ffma2_acc(e##I, bc2(C0a.y), G[(KC + 1) % 6][I]);                            \
+    ffma2_acc(e##I, bc2(C0a.z), G[(KC + 2) % 6][I]);                            \
+    ffma2_acc(e##I, bc2(C0a.w), G[(KC + 3) % 6][I]);                            \
+    ffma2_acc(e##I, bc2(C0b.x), G[(KC + 4) % 6][I]);                            \
+    ffma2_acc(e##I, bc2(C0b.y), G[(KC + 5) % 6][I]);
 #define COL_I_LOAD(X, U)                                                                           \
     {                                                                                              \
         const float* R = Rb + (U) * CRECW;                                                         \
@@ -468,6 +521,9 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
         X##C0b = *reinterpret_cast<const float2*>(R + 16);                                         \
         X##w = R[20 + lw];                                                                         \
     }
+    // the 32 partial sums of a sample go to row (sample mod PB) of the transpose buffer; every PB samples the rows are
+    // summed (lane -> (sample, part of the row)) and stored -- folding them with shuffles first was measured: each fold
+    // step costs ~40 us
 #define COL_I_BODY(KC, X, U)                                                                       \
     {                                                                                              \
         COL_DOT_ROW(KC, 0, X##C0a, X##C0b)                                                         \
@@ -476,60 +532,75 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
         P2 acc = fmul2(bc2(X##C1.x), e0);                                                         \
         ffma2_acc(acc, bc2(X##C1.y), e1);                                                          \
         ffma2_acc(acc, bc2(X##C1.z), e2);                                                          \
-        pbuf[(U) * PBUF_PITCH + lane] = fmul2(bc2(X##w), acc);                                     \
+        pbuf[((U) & (PB - 1)) * PBUF_PITCH + lane] = fmul2(bc2(X##w), acc);                        \
     }
-        // phase KC: plane p sits in ring slot KC.  Take every sample whose first plane is p (counted loop over the run,
-        // as in the scatter), then replace plane p by plane p + 8 (consumed two window moves later) and, optionally,
-        // ask L2 for a plane further ahead.
+#if COL_I_PAIR       // two samples per trip, all loads ahead of the math; needs PB == CCH (one reduction per chunk)
+#define COL_I_RUN(KC)                                                                              \
+    _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                           \
+        COL_I_LOAD(a, u)                                                                           \
+        COL_I_LOAD(b, u + 1)                                                                       \
+        COL_I_BODY(KC, a, u)                                                                       \
+        COL_I_BODY(KC, b, u + 1)                                                                   \
+    }                                                                                              \
+    if (n) {                                                                                       \
+        COL_I_LOAD(a, u)                                                                           \
+        COL_I_BODY(KC, a, u)                                                                       \
+        ++u;                                                                                       \
+    }
+#else
+#define COL_I_RUN(KC)                                                                              \
+    _Pragma("unroll 1") for (; n > 0; --n, ++u) {                                                  \
+        COL_I_LOAD(a, u)                                                                           \
+        COL_I_BODY(KC, a, u)                                                                       \
+        if (PB < CCH && (u & (PB - 1)) == PB - 1) reduce_group(u - (PB - 1));                      \
+    }
+#endif
+        // phase KC: plane p sits in window slot KC.  Take every sample whose first plane is p (counted loop over the run;
+        // the first plane and the remaining run length of the next sample are kept in registers, so a plane without
+        // samples costs no shared-memory load), then plane p + 6 enters slot KC from the shared-memory ring and the
+        // copy of plane p + 6 + PRING is started into the ring entry it leaves.
 #define COL_I_PHASE(KC)                                                                            \
     case KC: {                                                                                     \
         if (u == ns) { K = KC; goto chunk_done; }                                                  \
-        {                                                                                          \
+        if (pnext == p) {                                                                          \
+            int n = min(nrun, ns - u);                                                             \
+            COL_I_RUN(KC)                                                                          \
+            if (u == ns) { K = KC; goto chunk_done; }                                              \
             const int2 pr = *reinterpret_cast<const int2*>(Rb + u * CRECW + 18);   /* p0, run */   \
             pnext = pr.x;                                                                          \
-            if (pnext == p) {                                                                      \
-                int n = min(pr.y, ns - u);                                                         \
-                _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                                   \
-                    COL_I_LOAD(a, u)                                                               \
-                    COL_I_LOAD(b, u + 1)                                                           \
-                    COL_I_BODY(KC, a, u)                                                           \
-                    COL_I_BODY(KC, b, u + 1)                                                       \
-                }                                                                                  \
-                if (n) {                                                                           \
-                    COL_I_LOAD(a, u)                                                               \
-                    COL_I_BODY(KC, a, u)                                                           \
-                    ++u;                                                                           \
-                }                                                                                  \
-                if (u == ns) { K = KC; goto chunk_done; }                                          \
-                pnext = __float_as_int(Rb[u * CRECW + 18]);                                        \
-            }                                                                                      \
+            nrun = pr.y;                                                                           \
         }                                                                                          \
         {                                                                                          \
-            int pl = p + IRING;                                                                    \
+            cp_async_wait<PRING - 1>();                                                            \
+            const unsigned sa = pring + ((unsigned)(p + 6 + 12 * PRING) % PRING) * PSLOT;                 \
+            if (!(g.dbg & 1)) {                                                                    \
+                _Pragma("unroll") for (int i = 0; i < CNR; ++i) G[KC][i] = lds64(sa + i * 256);    \
+            }                                                                                      \
+            int pl = p + 6 + PRING;                                                                \
             if (pl >= g.K0) pl -= g.K0;                                                            \
             const int off = pl * KK;                                                               \
             if (!(g.dbg & 1)) {                                                                    \
-                _Pragma("unroll") for (int i = 0; i < CNR; ++i) G[KC][i] = ldg_u64(cell_at(cell[i], off)); \
+                _Pragma("unroll") for (int i = 0; i < CNR; ++i) cp_async8(sa + i * 256, cell_at(cell[i], off)); \
             }                                                                                      \
-            if (g.pf_ahead) {                                                                      \
-                int pf = pl + g.pf_ahead;                                                          \
-                if (pf >= g.K0) pf -= g.K0;                                                        \
-                if (pf >= g.K0) pf = pl;    /* tiny grids */                                       \
-                const int offp = pf * KK;                                                          \
-                _Pragma("unroll") for (int i = 0; i < CNR; ++i) prefetch_l2(cell_at(cell[i], offp)); \
-            }                                                                                      \
+            cp_async_commit();                                                                     \
             ++p;                                                                                   \
-            if (pnext - p >= IRING) {   /* jump: nothing in the ring is of use, prime it again */  \
-                p = pnext - IRING;                                                                 \
-                K = pnext % IRING;                                                                 \
+            if (pnext - p > 6 + PRING) {    /* jump: nothing on its way is of use, prime the window again */ \
+                cp_async_wait_all();                                                               \
+                p = pnext - 6 - PRING;                                                             \
+                K = mod6(p);                                                                       \
                 continue;                                                                          \
             }                                                                                      \
         }                                                                                          \
     }
 
-        float4 aC1, aC0a, bC1, bC0a;
-        float2 aC0b, bC0b;
-        float aw, bw;
+        float4 aC1, aC0a;
+        float2 aC0b;
+        float aw;
+#if COL_I_PAIR
+        float4 bC1, bC0a;
+        float2 bC0b;
+        float bw;
+#endif
         for (;;) {                      // chunks
             {
                 s0 = wi.begin + kc * CCH;
@@ -542,16 +613,18 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
                 ns = min(CCH, wi.end - s0);
                 mbar_wait(&mbar[b], ((gk + kc) / INB) & 1);
                 Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
-                // phase and original index of sample `lane` of the chunk (used after the reduction): they come with the
+                // phase and original index of the chunk's samples (used after the reduction): they come with the
                 // records -- a global load here kept the long scoreboard busy across the chunk boundary
-                if (lane < ns) sd = reinterpret_cast<const float4*>(sbuf + b * SIDE_BYTES)[lane];
+                Sb = reinterpret_cast<const float4*>(sbuf + b * SIDE_BYTES);
                 u = 0;
                 ++kc;
+                const int2 pr = *reinterpret_cast<const int2*>(Rb + 18);
+                pnext = pr.x;
+                nrun = pr.y;
             }
-            if (!started) {             // prime the ring: eight empty phases load planes p0 .. p0 + 7
-                const int pf = __float_as_int(Rb[18]);
-                p = pf - IRING;
-                K = pf % IRING;
+            if (!started) {             // prime the window: 6 + PRING empty phases bring in planes pnext .. pnext + 5
+                p = pnext - 6 - PRING;
+                K = mod6(p);
                 started = true;
             }
             for (;;) {                  // phases
@@ -562,38 +635,18 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
                     COL_I_PHASE(3)
                     COL_I_PHASE(4)
                     COL_I_PHASE(5)
-                    COL_I_PHASE(6)
-                    COL_I_PHASE(7)
-#if COL_IRING == 10
-                    COL_I_PHASE(8)
-                    COL_I_PHASE(9)
-#endif
                 }
                 K = 0;
             }
         chunk_done:
-            // ---- reduce the 32 partial sums of every sample of the chunk: lane -> (sample, half) ----
-            __syncwarp();
-            {
-                const int su = lane & 15, h = lane >> 4;
-                const P2* pb = pbuf + su * PBUF_PITCH + h * 16;
-                float2 sum = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int l = 0; l < 16; ++l) {
-                    const float2 v = pb[l];
-                    sum.x += v.x;
-                    sum.y += v.y;
-                }
-                sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 16);
-                sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 16);
-                if (lane < ns) y[(long long)__float_as_int(sd.z) * nb + c] = cmul(make_float2(sd.x, sd.y), sum);
-            }
-            __syncwarp();
+            if (PB == CCH) reduce_group(0);
+            else if (ns & (PB - 1)) reduce_group(ns & ~(PB - 1));   // the last, partial group of an item's last chunk
             if (kc == nchunks) break;
         }
         gk += nchunks;
     }
 #undef COL_I_PHASE
+#undef COL_I_RUN
 #undef COL_I_BODY
 #undef COL_I_LOAD
 #undef COL_DOT_ROW
@@ -634,17 +687,15 @@ bool col3d_supported(const Geom& g) {
         if (g.J[d] != 6) return false;
     return g.K[0] >= 6 && g.K[1] >= CROWS && g.K[2] >= CCOLS;
 }
-// the gather's register ring runs two planes ahead of the window: planes up to K0 + 7 are wrapped with one subtraction
-bool col3d_interp_supported(const Geom& g) { return col3d_supported(g) && g.K[0] >= IRING; }
+// the gather's plane copies run PRING planes ahead of the window: planes up to K0 + 5 + PRING are wrapped with one subtraction
+bool col3d_interp_supported(const Geom& g) { return col3d_supported(g) && g.K[0] >= 6 + PRING; }
 
 static ColGeom col_geom(const Geom& g) {
     ColGeom c;
     c.K0 = g.K[0]; c.K1 = g.K[1]; c.K2 = g.K[2];
     c.nq2 = (g.K[2] + CT2 - 1) / CT2;
-    c.pf_ahead = 0;
     c.dbg = 0;
     if (const char* e = getenv("B200NUFFT_COL_DBG")) c.dbg = atoi(e);
-    if (const char* e = getenv("B200NUFFT_COL_PF")) c.pf_ahead = std::max(0, atoi(e));    // tuning knob
     c.Kprod = g.Kprod;
     return c;
 }
@@ -701,7 +752,8 @@ int col3d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cuda
     rc = col_counters(p, nb);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(p->d_ccount, 0, sizeof(int) * nb, st));
-    dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, 4)), nb);
+    static const int ictas = [] { const char* e = getenv("B200NUFFT_COL_ICTAS"); return e ? std::max(1, atoi(e)) : COL_I_CTAS; }();   // tuning knob
+    dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nb, ictas)), nb);
     k_interp_col<<<gr, CWARPS * 32, CWARPS * IWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
                                                                p->d_crec, p->d_cside, grid, y, nb);
     LAUNCH_CHECK();

@@ -22,6 +22,8 @@
 // gridding kernel produces (col3d.cu), so that k-space solvers can iterate on modulated vectors without converting.
 // The staged box then only needs the wrap signs (-1)^(N-1) of neighbours that wrap around the periodic grid, every
 // interpolation weight is real, and the sample's phase becomes P * prod_d e^{i s_d (1 - k_d)} (k_d = first neighbour).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -296,9 +298,12 @@ bool tiled_supported(const Geom& g) {
 }
 
 int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaStream_t st, bool modulated) {
+    // tuning knob: extra dynamic shared memory per CTA (lowers the number of resident CTAs per SM; co-scheduling experiments)
+    static const size_t pad = [] { const char* e = getenv("B200NUFFT_IT_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();
+    const size_t smem = SMEM_BYTES + pad;
     if (!p->attr_interp) {      // once per plan (the attribute is per device, plans are per device)
-        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_interp_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         p->attr_interp = true;
     }
     if (modulated && !p->d_mod) {
@@ -308,9 +313,9 @@ int interp_tiled_launch(b200nufft_plan_t p, const float2* grid, float2* y, int n
     if (p->n_work == 0) return B200_OK;
     dim3 gr(p->n_work, nb);
     if (modulated)
-        k_interp_tiled<true><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_trec, grid, y, nb, p->d_mod);
+        k_interp_tiled<true><<<gr, NTHREADS, smem, st>>>(p->g, p->d_work, p->d_trec, grid, y, nb, p->d_mod);
     else
-        k_interp_tiled<false><<<gr, NTHREADS, SMEM_BYTES, st>>>(p->g, p->d_work, p->d_trec, grid, y, nb, nullptr);
+        k_interp_tiled<false><<<gr, NTHREADS, smem, st>>>(p->g, p->d_work, p->d_trec, grid, y, nb, nullptr);
     LAUNCH_CHECK();
     return B200_OK;
 }

@@ -48,11 +48,14 @@ constexpr int CWARPS = 4;                 // warps per CTA (each warp works on i
 constexpr int REC_BYTES = CCH * CRECW * 4;            // 2048
 constexpr int YS_BYTES = 160;                         // up to 18 pre-gathered values (8 B) per chunk, 16-byte multiple
 constexpr int GWARP_BYTES = 4608;                     // scatter: 2 * REC + 2 * YS + dummy record + mbar, rounded to 128
+#ifndef COL_I_LOADS
+#define COL_I_LOADS 1       // 0: skip the plane copies (timing experiments; wrong results)
+#endif
 #ifndef COL_I_CTAS
-#define COL_I_CTAS 6
+#define COL_I_CTAS 4
 #endif
 #ifndef COL_I_PRING
-#define COL_I_PRING 3
+#define COL_I_PRING 4
 #endif
 #ifndef COL_I_PB
 #define COL_I_PB 16
@@ -80,7 +83,6 @@ static_assert(PRING >= 1 && PRING <= 6 && (PB == 8 || PB == 16) && CCH % PB == 0
 
 struct ColGeom {
     int K0, K1, K2, nq2;
-    int dbg;                    // experiments (B200NUFFT_COL_DBG): bit 0 = skip the REDs / plane loads
     long long Kprod;
 };
 
@@ -169,8 +171,8 @@ __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M
 // ---------------------------------------------------------------------------------------------------------
 // gridding (scatter): produces the phase-modulated grid
 // ---------------------------------------------------------------------------------------------------------
-#ifndef COL_S_PAIR
-#define COL_S_PAIR 1
+#ifndef COL_S_RED
+#define COL_S_RED 1         // 0: skip the REDs (timing experiments; wrong results)
 #endif
 #ifndef COL_S_CTAS
 #define COL_S_CTAS 4
@@ -241,8 +243,10 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
             for (int i = 0; i < CNR; ++i) A[s][i] = make_float2(0.f, 0.f);
         int kc = 0, u = 0, ns = 0;      // next chunk, sample inside the chunk, samples of the chunk
         int K = 0;                      // phase = slot of the window's first plane
-        int p = 0, pw = 0, poff = 0;    // first plane of the window, the same wrapped into the grid, its element offset
-        int plim = 0, pnext = 0;        // last plane that holds contributions; first plane of the next sample
+        int p = 0, pw = 0;              // first plane of the window, the same wrapped into the grid
+        int plim = 0;                   // last plane that holds contributions
+        int pnext = 0, nrun = 0;        // first plane of the next sample and what is left of its run (INT_MAX: no sample left)
+        float2 *cp0 = cell[0], *cp1 = cell[1], *cp2 = cell[2];   // this lane's cells in plane pw
         bool started = false;
         const float* Rb = dummy;
         const float2* Y = reinterpret_cast<const float2*>(dummy);
@@ -274,62 +278,46 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         COL_ACC_ROW(KC, 1, t1, X##C0a, X##C0b)                                                     \
         COL_ACC_ROW(KC, 2, t2, X##C0a, X##C0b)                                                     \
     }
-#if COL_S_PAIR
-#define COL_S_RUN(KC)                                                                              \
-    _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                           \
-        COL_S_LOAD(a, u)                                                                           \
-        COL_S_LOAD(b, u + 1)                                                                       \
-        COL_S_BODY(KC, a)                                                                          \
-        COL_S_BODY(KC, b)                                                                          \
-    }                                                                                              \
-    if (n) {                                                                                       \
-        COL_S_LOAD(a, u)                                                                           \
-        COL_S_BODY(KC, a)                                                                          \
-        ++u;                                                                                       \
-    }
-#else
-#define COL_S_RUN(KC)                                                                              \
-    _Pragma("unroll 1") for (; n > 0; --n, ++u) {                                                  \
-        COL_S_LOAD(a, u)                                                                           \
-        COL_S_BODY(KC, a)                                                                          \
-    }
-#endif
-        // phase KC: plane p sits in slot KC.  Take every sample whose first plane is p -- the record carries the length of
-        // the run of samples that share its (column, first plane), so this is a counted loop (two samples per trip, all
-        // loads ahead of the math) instead of a load -> compare -> branch chain per sample -- then retire plane p.
+        // phase KC: plane p sits in slot KC.  (pnext, nrun) = first plane and remaining run length of the next sample are
+        // carried in registers, so a plane without samples costs no shared-memory load and no chunk test.  Take every
+        // sample whose first plane is p -- a counted loop (two samples per trip, all loads ahead of the math) -- then
+        // retire plane p: three vector REDs through this lane's running cell pointers, which then move on one plane.
+        // Invariant at a phase start: u < ns, or pnext == INT_MAX (all samples of the item taken, the window drains).
 #define COL_S_PHASE(KC)                                                                            \
     case KC: {                                                                                     \
-        if (u == ns) { K = KC; goto chunk_done; }                                                  \
-        {                                                                                          \
+        if (pnext == p) {                                                                          \
+            int n = min(nrun, ns - u);                                                             \
+            _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                   \
+                COL_S_LOAD(a, u)                                                                   \
+                COL_S_LOAD(b, u + 1)                                                               \
+                COL_S_BODY(KC, a)                                                                  \
+                COL_S_BODY(KC, b)                                                                  \
+            }                                                                                      \
+            if (n) {                                                                               \
+                COL_S_LOAD(a, u)                                                                   \
+                COL_S_BODY(KC, a)                                                                  \
+                ++u;                                                                               \
+            }                                                                                      \
+            plim = p + 5;                                                                          \
+            if (u == ns) { K = KC; goto chunk_done; }       /* the run may go on in the next chunk */ \
             const int2 pr = *reinterpret_cast<const int2*>(Rb + u * CRECW + 18);   /* p0, run */   \
             pnext = pr.x;                                                                          \
-            if (pnext == p) {                                                                      \
-                int n = min(pr.y, ns - u);                                                         \
-                _Pragma("unroll 1") for (; n >= 2; n -= 2, u += 2) {                                                   \
-                    COL_S_LOAD(a, u)                                                               \
-                    COL_S_LOAD(b, u + 1)                                                           \
-                    COL_S_BODY(KC, a)                                                              \
-                    COL_S_BODY(KC, b)                                                              \
-                }                                                                                  \
-                if (n) {                                                                           \
-                    COL_S_LOAD(a, u)                                                               \
-                    COL_S_BODY(KC, a)                                                              \
-                    ++u;                                                                           \
-                }                                                                                  \
-                plim = p + 5;                                                                      \
-                if (u == ns) { K = KC; goto chunk_done; }       /* the run may go on in the next chunk */ \
-                pnext = __float_as_int(Rb[u * CRECW + 18]);                                        \
-            }                                                                                      \
+            nrun = pr.y;                                                                           \
         }                                                                                          \
-        _Pragma("unroll") for (int i = 0; i < CNR; ++i) {                                          \
-            if (!(g.dbg & 1)) red_v2(cell_at(cell[i], poff), A[KC][i]);                            \
-            A[KC][i] = make_float2(0.f, 0.f);                                                                       \
+        if (COL_S_RED) {                                                                           \
+            red_v2(cp0, A[KC][0]);                                                                 \
+            red_v2(cp1, A[KC][1]);                                                                 \
+            red_v2(cp2, A[KC][2]);                                                                 \
         }                                                                                          \
-        ++p; ++pw; poff += KK;                                                                     \
-        if (pw == g.K0) { pw = 0; poff = 0; }                                                      \
+        _Pragma("unroll") for (int i = 0; i < CNR; ++i) A[KC][i] = make_float2(0.f, 0.f);          \
+        cp0 += KK; cp1 += KK; cp2 += KK;                                                           \
+        ++p;                                                                                       \
+        if (++pw == g.K0) { pw = 0; cp0 -= g.Kprod; cp1 -= g.Kprod; cp2 -= g.Kprod; }              \
         if (p > plim) {                 /* nothing left in the window */                           \
             if (pnext == INT_MAX) goto item_done;                                                  \
-            p = pnext; pw = pnext; poff = pnext * KK; K = pnext % 6;                               \
+            const long long d = (long long)(pnext - p) * KK;    /* p < K0 here: pw == p */         \
+            cp0 += d; cp1 += d; cp2 += d;                                                          \
+            p = pnext; pw = pnext; K = pnext % 6;                                                  \
             continue;                                                                              \
         }                                                                                          \
     }
@@ -339,11 +327,8 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         float aw, bw;
         P2 ayv, byv;
         for (;;) {                      // chunks
-            if (kc == nchunks) {        // all samples taken: the dummy record makes the phases drain the window
-                Rb = dummy;
-                Y = reinterpret_cast<const float2*>(dummy);
-                ns = 1;
-                u = 0;
+            if (kc == nchunks) {        // all samples taken: the phases only retire what is left in the window
+                pnext = INT_MAX;
             } else {
                 const int s = wi.begin + kc * CCH;
                 const unsigned b = (gk + kc) & 1;
@@ -358,12 +343,16 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
                 ns = min(CCH, wi.end - s);
                 u = 0;
                 ++kc;
+                const int2 pr = *reinterpret_cast<const int2*>(Rb + 18);
+                pnext = pr.x;
+                nrun = pr.y;
             }
             if (!started) {
-                p = __float_as_int(Rb[18]);
+                p = pnext;
                 K = p % 6;
                 pw = p;
-                poff = p * KK;
+                const long long d = (long long)p * KK;
+                cp0 += d; cp1 += d; cp2 += d;
                 plim = p + 5;
                 started = true;
             }
@@ -385,7 +374,6 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         __syncwarp();
     }
 #undef COL_S_PHASE
-#undef COL_S_RUN
 #undef COL_S_BODY
 #undef COL_S_LOAD
 #undef COL_ACC_ROW
@@ -573,13 +561,13 @@ k_interp_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __re
         {                                                                                          \
             cp_async_wait<PRING - 1>();                                                            \
             const unsigned sa = pring + ((unsigned)(p + 6 + 12 * PRING) % PRING) * PSLOT;                 \
-            if (!(g.dbg & 1)) {                                                                    \
+            if (COL_I_LOADS) {                                                                    \
                 _Pragma("unroll") for (int i = 0; i < CNR; ++i) G[KC][i] = lds64(sa + i * 256);    \
             }                                                                                      \
             int pl = p + 6 + PRING;                                                                \
             if (pl >= g.K0) pl -= g.K0;                                                            \
             const int off = pl * KK;                                                               \
-            if (!(g.dbg & 1)) {                                                                    \
+            if (COL_I_LOADS) {                                                                    \
                 _Pragma("unroll") for (int i = 0; i < CNR; ++i) cp_async8(sa + i * 256, cell_at(cell[i], off)); \
             }                                                                                      \
             cp_async_commit();                                                                     \
@@ -694,8 +682,6 @@ static ColGeom col_geom(const Geom& g) {
     ColGeom c;
     c.K0 = g.K[0]; c.K1 = g.K[1]; c.K2 = g.K[2];
     c.nq2 = (g.K[2] + CT2 - 1) / CT2;
-    c.dbg = 0;
-    if (const char* e = getenv("B200NUFFT_COL_DBG")) c.dbg = atoi(e);
     c.Kprod = g.Kprod;
     return c;
 }
@@ -760,8 +746,8 @@ int col3d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cuda
     return B200_OK;
 }
 
-// grid receives the phase-modulated adjoint (it is zeroed here, by the pre-pass)
-int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st) {
+// grid receives the phase-modulated adjoint (it is zeroed here, by the pre-pass, unless the caller hands in a zeroed one)
+int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool prezeroed) {
     int rc = col_attrs(p);
     if (rc) return rc;
     const long long nel = p->g.Kprod * nb;
@@ -779,8 +765,8 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
     rc = col_counters(p, nb);
     if (rc) return rc;
     // float4 stores need a 16-byte aligned grid and an even element count; otherwise plain memset
-    const bool vec = (reinterpret_cast<uintptr_t>(grid) & 15) == 0 && (nel & 1) == 0;
-    if (!vec) CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * nel, st));
+    const bool vec = !prezeroed && (reinterpret_cast<uintptr_t>(grid) & 15) == 0 && (nel & 1) == 0;
+    if (!vec && !prezeroed) CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * nel, st));
     {
         // sized from the larger of the two jobs (grid zero-fill, data gather), capped: grid-stride loops inside
         const int TB = 256;

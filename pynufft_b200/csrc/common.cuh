@@ -197,6 +197,13 @@ struct b200nufft_plan_s {
     int grid_nb = 0;
     float2* d_grid2 = nullptr;      // coil-major FFT scratch of the batch-innermost 2-D path (sweep2d.cu)
     int grid2_nb = 0;
+    // adjoint grid of the column-sweep path, kept zeroed BETWEEN calls: the zero-fill of the next call is issued on a
+    // side stream behind the inverse FFT passes of this one (stages.cu adjoint_impl), off the caller's stream
+    float2* d_gridz = nullptr;
+    int gridz_nb = 0;
+    bool gridz_clean = false;       // a zero-fill is in flight / done on zs; gridz_ev marks its end
+    cudaStream_t zs = nullptr;
+    cudaEvent_t gridz_ev = nullptr, gridz_use = nullptr;
     // host staging for the *_host entry points
     float2* d_xin = nullptr;
     float2* d_yio = nullptr;
@@ -250,7 +257,7 @@ int ensure_scratch2(b200nufft_plan_t p, int nb);
 // col3d.cu: register-resident column-sweep gridding (3-D, J = 6); the grid it produces is phase-modulated
 bool col3d_supported(const Geom& g);
 // zeroes the grid itself (inside its pre-pass kernel)
-int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st);
+int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st, bool prezeroed = false);
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st);
 // register-resident column-sweep gather on the phase-modulated grid (needs K0 >= 8)
 bool col3d_interp_supported(const Geom& g);

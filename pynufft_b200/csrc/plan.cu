@@ -740,6 +740,13 @@ extern "C" int b200nufft_plan_destroy(b200nufft_plan_t p) {
     cudaFree(p->d_xc);
     cudaFree(p->d_grid);
     cudaFree(p->d_grid2);
+    if (p->zs) {
+        cudaStreamSynchronize(p->zs);
+        cudaEventDestroy(p->gridz_ev);
+        cudaEventDestroy(p->gridz_use);
+        cudaStreamDestroy(p->zs);
+    }
+    cudaFree(p->d_gridz);
     cudaFree(p->d_fbi_tw);
     cudaFree(p->d_fbi_rev);
     cudaFree(p->d_xin);

@@ -265,10 +265,15 @@ int col3d_interp(b200nufft_plan_t p, const float2* grid_mod, float2* y, int nb, 
 int col3d_modulate(b200nufft_plan_t p, const float2* in, float2* out, int nb, cudaStream_t st);
 // the gridding output is phase-modulated iff the column-sweep kernel runs (gridding variant "auto")
 static inline bool gridding_modulated(const b200nufft_plan_s* p) { return p->has_col && p->gridding_variant == 0; }
-// interp variant 3: the column-sweep gather (reads the modulated grid).  Measured on configuration 3 it is slower than
-// the tiled gather (272 us against 254 us), so "auto" (0) keeps the tiled kernel; the variant stays selectable.
+// interp variant 3: the column-sweep gather everywhere (a true grid is modulated first).  "auto" (0) uses it wherever the
+// grid is phase-modulated already -- forward() on the fused FFT passes, the k-space solvers -- since its planes arrive
+// through a cp.async ring (237 us against 252 us for the tiled gather at configuration 3); true grids handed to the
+// interp stage stay on the tiled gather, which needs no modulation pass.
 static inline bool interp_uses_col(const b200nufft_plan_s* p) {
     return p->has_col && p->d_mod && p->interp_variant == 3 && col3d_interp_supported(p->g);
+}
+static inline bool interp_col_on_modulated(const b200nufft_plan_s* p) {
+    return p->has_col && p->d_mod && (p->interp_variant == 0 || p->interp_variant == 3) && col3d_interp_supported(p->g);
 }
 // the gather can read that modulated grid directly (k-space solvers iterate on modulated vectors): column-sweep gather,
 // or the tiled gather's MOD instantiation

@@ -109,7 +109,7 @@ int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaS
             b200_set_error("interp: this plan / variant cannot read a phase-modulated grid");
             return B200_ERR_UNSUPPORTED;
         }
-        if (interp_uses_col(p)) return col3d_interp(p, grid, y, nb, st);
+        if (interp_col_on_modulated(p)) return col3d_interp(p, grid, y, nb, st);
         return interp_tiled_launch(p, grid, y, nb, st, true);
     }
     if (use_bi(p, nb)) return sweep2d_interp(p, grid, y, nb, st);             // batch-innermost grid

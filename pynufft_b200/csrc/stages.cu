@@ -424,7 +424,9 @@ static int forward_impl(b200nufft_plan_t p, const float2* x, int x_single, const
     if (rc) return rc;
     // the column-sweep gather reads the phase-modulated grid: the forward FFT passes produce it directly
     // (3-D); the 2-D multi-coil FFT pass along dim 0 writes the modulated grid the row-sweep gather reads
-    const bool mod = (interp_uses_col(p) && !use_bi(p, nb)) || bi_fused_mod(p, nb);
+    // ("auto": only where the fused passes emit the modulated grid for free)
+    const bool col_auto = p->interp_variant == 0 && interp_col_on_modulated(p) && p->fft_variant != 1 && fft256_supported(p->g);
+    const bool mod = ((interp_uses_col(p) || col_auto) && !use_bi(p, nb)) || bi_fused_mod(p, nb);
     rc = pad_fft_impl(p, reinterpret_cast<const b200_c64*>(x), reinterpret_cast<b200_c64*>(p->d_grid), nb, 1,
                       x_single, reinterpret_cast<const b200_c64*>(sens), stream, mod);
     if (rc) return rc;

@@ -16,7 +16,7 @@ for r in rows[2:]:
 rows = run('source'); hdr = rows[1]
 ia, isrc, isamp, iex = hdr.index('Address'), hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instructions Executed')
 iw, iid = hdr.index('L1 Wavefronts Shared'), hdr.index('L1 Wavefronts Shared Ideal')
-data = [r for r in rows[2:] if len(r) > iw]
+data = [r for r in rows[2:] if len(r) > iw and r[isamp].strip().isdigit()]
 base = int(data[0][ia], 16)
 tot = sum(int(r[isamp]) for r in data); totex = sum(int(r[iex]) for r in data)
 print('total samples', tot, 'instructions', totex, 'shared wavefronts', sum(int(r[iw]) for r in data), 'ideal', sum(int(r[iid]) for r in data))

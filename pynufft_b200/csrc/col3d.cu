@@ -10,15 +10,17 @@
 //  * the footprint of a sample lies inside the 9 x 10 box of its column (4 + 5 rows, 5 + 5 columns).  Lane (g, c),
 //    g = 0..2, c = 0..9 (30 lanes), owns the box cells (rows g, g + 3, g + 6; column c) of the planes of the current
 //    window [p, p + 6).  Samples arrive in plane order, so the window only slides forward, one plane at a time;
-//  * STATIC PLANE PHASES: the code is unrolled over the residue of the window's first plane (p mod 6 for the scatter,
-//    p mod 8 for the gather, whose register ring also holds the two planes that are still in flight), so that inside a
-//    phase every accumulator / ring slot is a fixed register and the sample's dim-0 weights c0[j] need no rotation.
-//    A phase = "take every sample whose first plane is p, then retire plane p" and falls through into the next one;
-//  * scatter: the retired plane is flushed by ALL lanes at once, three 8-byte REDs per lane that cover three 80-byte
-//    row segments per instruction, and its registers are cleared.  gather: the retired plane's registers receive
-//    plane p + 8 by three 8-byte loads per lane that are consumed two window moves later (the L2 latency is covered
-//    by the samples in between and by the other warps); the 30 partial sums of a sample go through a 16-sample
-//    shared-memory transpose;
+//  * STATIC PLANE PHASES: the code is unrolled over the residue of the window's first plane (p mod 6), so that inside a
+//    phase every accumulator / window slot is a fixed register and the sample's dim-0 weights c0[j] need no rotation.
+//    A phase = "take every sample whose first plane is p, then retire plane p" and falls through into the next one; the
+//    first plane and the remaining run length of the NEXT sample are carried in registers, so a plane without samples
+//    costs no shared-memory load and no chunk test;
+//  * scatter: the retired plane is flushed by ALL lanes at once, three 8-byte REDs per lane (running cell pointers) that
+//    cover three 80-byte row segments per instruction, and its registers are cleared.  gather: the retired plane's
+//    registers receive plane p + 6 from a per-warp shared-memory ring that 8-byte cp.async copies fill PRING planes
+//    ahead of the window (each lane fetches and reads back its own three cells, so the per-thread cp.async groups are the
+//    only synchronisation): the L2 / DRAM latency of a plane is covered without registers that hold loads in flight;
+//    the 30 partial sums of a sample go through a 16-sample shared-memory transpose;
 //  * a sample is 5 LDS + 22 packed FP32 instructions per lane: the record holds the dim-1 weights as a zero-padded
 //    table over the box rows and the dim-2 weights zero-padded over the box columns, all REAL, because the grid these
 //    kernels work on is phase-modulated, G'[g] = G[g] * prod_d e^{i s_d g_d} (s_d = gamma_d (N_d - 1) / 2), which turns
@@ -141,8 +143,11 @@ __device__ __forceinline__ int next_item(int* counter, int lane) {
 }
 
 // Pre-pass of the scatter, one kernel: ys[c][i] = conj(P''_i) * y[perm[i], c] (8-byte slots, coil stride Mpad), the grid
-// zero-fill (the gather is latency-bound on the random reads of y and leaves the bandwidth to the stores) and the reset
-// of the persistent kernel's work counters.
+// zero-fill (when the caller's grid is not known to be zero) and the reset of the persistent kernel's work counters.
+// The data gather is a chain of two dependent loads per sample (side entry -> y[perm]): a thread takes GU samples at
+// a time, all side loads first, then all y loads (four independent chains in flight per thread), and the zero-fill
+// stores of the thread are issued between the two so that the store stream covers part of the latency.
+constexpr int GU = 4;
 __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M, long long Mpad,
                                     const float2* __restrict__ y, float2* __restrict__ ys, int nb,
                                     float4* __restrict__ grid4, long long n4, int* __restrict__ counters) {
@@ -150,25 +155,42 @@ __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M
     const long long T = gridDim.x * (long long)blockDim.x;
     for (long long j = i; j < nb; j += T) counters[j] = 0;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    // the two dependent loads of a thread's first sample (side -> y[perm]) are issued around the first half of its
-    // zero-fill stores, so that the store stream covers their latency
-    const bool first = i < M;
-    float4 h = z;
-    if (first) h = __ldg(side + i);                     // P''.re, P''.im, original index
-    const long long half = (n4 / T / 2) * T;
-    for (long long j = i; j < half; j += T) grid4[j] = z;
-    float2 y0 = make_float2(0.f, 0.f);
-    if (first) y0 = y[(long long)__float_as_int(h.z) * nb];
-    for (long long j = half + i; j < n4; j += T) grid4[j] = z;
-    if (first) {
-        const int m = __float_as_int(h.z);
-        ys[i] = cmulc(make_float2(h.x, h.y), y0);
-        for (int c = 1; c < nb; ++c) ys[(long long)c * Mpad + i] = cmulc(make_float2(h.x, h.y), y[(long long)m * nb + c]);
-    }
-    for (long long s = i + T; s < M; s += T) {
-        const float4 hh = __ldg(side + s);
-        const int m = __float_as_int(hh.z);
-        for (int c = 0; c < nb; ++c) ys[(long long)c * Mpad + s] = cmulc(make_float2(hh.x, hh.y), y[(long long)m * nb + c]);
+    bool filled = false;
+    for (long long s0 = i; s0 < M || !filled; s0 += GU * T) {
+        float4 h[GU];
+        float2 v[GU];
+#pragma unroll
+        for (int j = 0; j < GU; ++j) {
+            const long long s = s0 + j * T;
+            h[j] = s < M ? __ldg(side + s) : z;                 // P''.re, P''.im, original index
+        }
+        if (!filled) {
+            const long long half = (n4 / T / 2) * T;
+            for (long long j = i; j < half; j += T) grid4[j] = z;
+#pragma unroll
+            for (int j = 0; j < GU; ++j) {
+                const long long s = s0 + j * T;
+                v[j] = s < M ? y[(long long)__float_as_int(h[j].z) * nb] : make_float2(0.f, 0.f);
+            }
+            for (long long j = half + i; j < n4; j += T) grid4[j] = z;
+            filled = true;
+        } else {
+#pragma unroll
+            for (int j = 0; j < GU; ++j) {
+                const long long s = s0 + j * T;
+                v[j] = s < M ? y[(long long)__float_as_int(h[j].z) * nb] : make_float2(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GU; ++j) {
+            const long long s = s0 + j * T;
+            if (s < M) {
+                const float2 ph = make_float2(h[j].x, h[j].y);
+                const long long m = __float_as_int(h[j].z);
+                ys[s] = cmulc(ph, v[j]);
+                for (int c = 1; c < nb; ++c) ys[(long long)c * Mpad + s] = cmulc(ph, y[m * nb + c]);
+            }
+        }
     }
 }
 
@@ -780,7 +802,7 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
     {
         // sized from the larger of the two jobs (grid zero-fill, data gather), capped: grid-stride loops inside
         const int TB = 256;
-        const long long want = std::max<long long>((p->M + TB - 1) / TB, vec ? (nel / 2 + TB * 8 - 1) / (TB * 8) : 1);
+        const long long want = std::max<long long>((p->M + TB * GU - 1) / (TB * GU), vec ? (nel / 2 + TB * 8 - 1) / (TB * 8) : 1);
         const unsigned nblk = (unsigned)std::min<long long>(std::max<long long>(want, 1), 148LL * 64);
         k_gather_sorted_col<<<nblk, TB, 0, st>>>(p->d_cside, p->M, Mpad, y, p->d_ys2, nb,
                                                  reinterpret_cast<float4*>(grid), vec ? nel / 2 : 0, p->d_ccount);

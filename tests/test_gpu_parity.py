@@ -207,6 +207,7 @@ def test_ragged_geometries(dev, geom):
     ((8, 8, 8), (16, 16, 16), 300),
     ((33, 31, 32), (66, 62, 64), 30000),
     ((5, 4, 5), (6, 9, 10), 200),                # smallest grid the column-sweep kernel takes: its box is the grid
+    ((32, 8, 10), (64, 16, 20), 130),            # a few samples per column: window jumps (gaps of > 10 planes), re-priming
 ])
 def test_gridding_kernels_agree_3d(dev, geom):
     """3-D J = 6: column-sweep (auto), tiled and generic gridding against the oracle, true-grid and fused paths"""

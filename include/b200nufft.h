@@ -202,7 +202,9 @@ int b200nufft_tv_bregman(b200_c64* AHyk, const b200_c64* zf, const b200_c64* AHy
 
 /* ---- tuning / introspection ---------------------------------------------------------------- */
 /* kernel variant selection: interp/gridding "auto" (0), "generic" (1), "tiled" (2); interp only: "column sweep" (3,
- * the register-resident gather of csrc/col3d.cu on the phase-modulated grid; 3-D, Jd = 6^3, Kd[0] >= 10) */
+ * the register-resident gather of csrc/col3d.cu on the phase-modulated grid; 3-D, Jd = 6^3, Kd[0] >= 10).  "auto"
+ * runs the column-sweep gather wherever the grid is phase-modulated already (forward on the fused FFT passes, the
+ * k-space solvers) and the tiled gather on true grids; 3 modulates a true grid first and sweeps everywhere */
 int b200nufft_set_variant(b200nufft_plan_t plan, int interp_variant, int gridding_variant);
 /* Column-sweep gridding (csrc/col3d.cu).  Plans for 3-D, Jd = 6^3 keep, next to the tile-sorted samples, a second
  * copy sorted by (4 x 5 column of first-neighbour cells, first plane) for the register-resident scatter kernel.

@@ -506,6 +506,7 @@ class NUFFT:
 
     def set_variant(self, interp=0, gridding=0):
         """0 auto, 1 generic kernels, 2 tiled kernels (error if the geometry is unsupported); interp=3 selects the
-        column-sweep gather (csrc/col3d.cu)."""
+        column-sweep gather (csrc/col3d.cu) everywhere; auto uses it on phase-modulated grids (forward on the fused
+        FFT passes, k-space solvers) and the tiled gather on true grids."""
         self._require_plan()
         _lib.check(self._lib.b200nufft_set_variant(self._plan, int(interp), int(gridding)))

@@ -314,7 +314,7 @@ k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const f
 #pragma unroll
         for (int i = 0; i < CH; ++i) A[s][i] = make_float2(0.f, 0.f);
     int kc = 0, u = 0, ns = 0;
-    int K = 0, p = 0, pw = 0, plim = 0, pnext = 0;
+    int K = 0, p = 0, pw = 0, plim = 0, pnext = 0, nrun = 0;
     bool started = false;
     const float* Rb = dummy;
     const float2* Y = sy;
@@ -346,21 +346,18 @@ k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const f
     // row p: demodulate, flush with REDs (128-byte runs: 16 coils of one cell), clear.
 #define SW2_S_PHASE(KC)                                                                            \
     case KC: {                                                                                     \
-        if (u == ns) { K = KC; goto chunk_done; }                                                  \
         const float2 f0r = MODG ? make_float2(1.f, 0.f) : __ldg(m0 + pw);   /* consumed at the flush below */ \
-        {                                                                                          \
+        if (pnext == p) {               /* (pnext, nrun): first row / remaining run of the next sample, in registers */ \
+            int n = min(nrun, ns - u);                                                             \
+            _Pragma("unroll 1") for (; n > 0; --n, ++u) {                                          \
+                SW2_LOAD(a, u)                                                                     \
+                SW2_S_BODY(KC, a, u)                                                               \
+            }                                                                                      \
+            plim = p + 5;                                                                          \
+            if (u == ns) { K = KC; goto chunk_done; }       /* the run may go on in the next chunk */ \
             const int2 pr = *reinterpret_cast<const int2*>(Rb + u * RECW + 6);     /* p0, run */   \
             pnext = pr.x;                                                                          \
-            if (pnext == p) {                                                                      \
-                int n = min(pr.y, ns - u);                                                         \
-                _Pragma("unroll 1") for (; n > 0; --n, ++u) {                                          \
-                    SW2_LOAD(a, u)                                                                 \
-                    SW2_S_BODY(KC, a, u)                                                           \
-                }                                                                                  \
-                plim = p + 5;                                                                      \
-                if (u == ns) { K = KC; goto chunk_done; }                                          \
-                pnext = __float_as_int(Rb[u * RECW + 6]);                                          \
-            }                                                                                      \
+            nrun = pr.y;                                                                           \
         }                                                                                          \
         {                                                                                          \
             const float2 f0 = make_float2(f0r.x, -f0r.y);                                          \
@@ -381,10 +378,8 @@ k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const f
     }
 
     for (;;) {                          // chunks
-        if (kc == nchunks) {            // all samples taken: the dummy record makes the phases drain the window
-            Rb = dummy;
-            ns = 1;
-            u = 0;
+        if (kc == nchunks) {            // all samples taken: the phases only retire what is left in the window
+            pnext = INT_MAX;
         } else {
             // records two chunks ahead, y rows one chunk ahead (every lane is done with the buffers they overwrite)
             __syncwarp();
@@ -405,9 +400,12 @@ k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const f
             ns = min(CCH, wi.end - (wi.begin + kc * CCH));
             u = 0;
             ++kc;
+            const int2 pr = *reinterpret_cast<const int2*>(Rb + 6);
+            pnext = pr.x;
+            nrun = pr.y;
         }
         if (!started) {
-            p = __float_as_int(Rb[6]);
+            p = pnext;
             K = p % 6;
             pw = p;
             plim = p + 5;
@@ -526,7 +524,7 @@ k_sw2_interp(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const flo
 #pragma unroll
         for (int i = 0; i < CH; ++i) G[s][i] = make_float2(0.f, 0.f);
     int kc = 0, u = 0, ns = 0;
-    int K = 0, p = 0, pnext = 0;
+    int K = 0, p = 0, pnext = 0, nrun = 0;
     int rfetched = 0;                   // rows < rfetched are in (or on their way to) the ring
     bool started = false;
     const float* Rb = nullptr;
@@ -568,20 +566,17 @@ k_sw2_interp(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const flo
     // registers and the ring is topped up (RS rows ahead of the window).
 #define SW2_I_PHASE(KC)                                                                            \
     case KC: {                                                                                     \
-        if (u == ns) { K = KC; goto chunk_done; }                                                  \
         const float2 f0n = row_factor(p + 6);              /* consumed when row p + 6 is taken below */ \
-        {                                                                                          \
+        if (pnext == p) {               /* (pnext, nrun): first row / remaining run of the next sample, in registers */ \
+            int n = min(nrun, ns - u);                                                             \
+            _Pragma("unroll 1") for (; n > 0; --n, ++u) {                                          \
+                SW2_LOAD(a, u)                                                                     \
+                SW2_I_BODY(KC, a, u)                                                               \
+            }                                                                                      \
+            if (u == ns) { K = KC; goto chunk_done; }                                              \
             const int2 pr = *reinterpret_cast<const int2*>(Rb + u * RECW + 6);     /* p0, run */   \
             pnext = pr.x;                                                                          \
-            if (pnext == p) {                                                                      \
-                int n = min(pr.y, ns - u);                                                         \
-                _Pragma("unroll 1") for (; n > 0; --n, ++u) {                                          \
-                    SW2_LOAD(a, u)                                                                 \
-                    SW2_I_BODY(KC, a, u)                                                           \
-                }                                                                                  \
-                if (u == ns) { K = KC; goto chunk_done; }                                          \
-                pnext = __float_as_int(Rb[u * RECW + 6]);                                          \
-            }                                                                                      \
+            nrun = pr.y;                                                                           \
         }                                                                                          \
         if (pnext - p > JUMP) {         /* long gap: restart the window at the next sample's first row */ \
             cp_async_wait<0>();                 /* rows in flight must land first */            \
@@ -609,9 +604,12 @@ k_sw2_interp(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const flo
             Rb = reinterpret_cast<const float*>(ws + b * REC_BYTES);
             u = 0;
             ++kc;
+            const int2 pr = *reinterpret_cast<const int2*>(Rb + 6);
+            pnext = pr.x;
+            nrun = pr.y;
         }
         if (!started) {
-            p = __float_as_int(Rb[6]);
+            p = pnext;
             K = p % 6;
             started = true;
             goto prime;

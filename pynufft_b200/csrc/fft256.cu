@@ -109,8 +109,11 @@ struct PassArgs {
 };
 
 // PASS: 1 = F1, 2 = F2, 3 = F3, 4 = I3, 5 = I2, 6 = I1
+#ifndef FFT256_MINB
+#define FFT256_MINB 4       // resident CTAs per SM the register allocation aims at (64 registers; measured 1 / 4 / 5 / 6: inverse passes 79 / 76 / 85 / 113 us)
+#endif
 template <int PASS>
-__global__ void __launch_bounds__(TPB) k_fft256(PassArgs a, const float2* __restrict__ twg) {
+__global__ void __launch_bounds__(TPB, FFT256_MINB) k_fft256(PassArgs a, const float2* __restrict__ twg) {
     constexpr int DIR = PASS <= 3 ? -1 : 1;
     constexpr bool CONTIG = (PASS == 1 || PASS == 6);
     __shared__ float2 sx[16 * TPITCH];

@@ -53,7 +53,7 @@ constexpr int CWARPS = 4;                 // warps per CTA (each warp works on i
 constexpr int COL_COILS = COL_COILS_MAX;  // coils that share one launch of the persistent kernels
 constexpr int REC_BYTES = CCH * CRECW * 4;            // 2048
 constexpr int YS_BYTES = 160;                         // up to 18 pre-gathered values (8 B) per chunk, 16-byte multiple
-constexpr int GWARP_BYTES = 4608;                     // scatter: 2 * REC + 2 * YS + dummy record + mbar, rounded to 128
+constexpr int GWARP_BYTES = 4608;                     // scatter: 2 * REC + 2 * YS + 128 spare + mbar, rounded to 128
 #ifndef COL_I_LOADS
 #define COL_I_LOADS 1       // 0: skip the plane copies (timing experiments; wrong results)
 #endif
@@ -211,7 +211,6 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* ws = smem_raw + warp * GWARP_BYTES;
     unsigned char* ybuf = ws + 2 * REC_BYTES;
-    float* dummy = reinterpret_cast<float*>(ws + 2 * REC_BYTES + 2 * YS_BYTES);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(ws + 2 * REC_BYTES + 2 * YS_BYTES + 128);
     const int c = blockIdx.y + coil0;
     float2* gc = grid + (long long)c * g.Kprod;
@@ -228,8 +227,6 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    // the record that ends every item: first plane = INT_MAX (the phases then only retire what is left)
-    dummy[lane] = lane == 18 ? __int_as_float(INT_MAX) : 0.f;
     __syncwarp();
     unsigned gk = 0;                                    // chunks consumed by this warp so far (mbarrier phases)
 
@@ -275,8 +272,8 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         int pnext = 0, nrun = 0;        // first plane of the next sample and what is left of its run (INT_MAX: no sample left)
         float2 *cp0 = cell[0], *cp1 = cell[1], *cp2 = cell[2];   // this lane's cells in plane pw
         bool started = false;
-        const float* Rb = dummy;
-        const float2* Y = reinterpret_cast<const float2*>(dummy);
+        const float* Rb = reinterpret_cast<const float*>(ws);      // set per chunk
+        const float2* Y = reinterpret_cast<const float2*>(ybuf);
 
 #define COL_ACC(SL, I, CV, TV) ffma2_acc(A[SL][I], bc2(CV), TV);
 #define COL_ACC_ROW(KC, I, TV, C0a, C0b)    \

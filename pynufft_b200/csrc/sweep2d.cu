@@ -41,6 +41,9 @@ constexpr int RECW = SW2_RECW;            // words per record: 20
 constexpr int CCH = 16;                   // samples per chunk
 constexpr int NCL = 16;                   // coils per warp
 constexpr int SWARPS = 4;                 // warps per CTA (each warp works on its own item)
+#ifndef SW2_CTAS
+#define SW2_CTAS 4                         // resident CTAs per SM the register allocation aims at
+#endif
 constexpr int REC_BYTES = CCH * RECW * 4;             // 1280
 constexpr int YCH_BYTES = CCH * NCL * 8;              // 2048: y rows of a chunk, 16 coils
 constexpr int GW_BYTES = 3 * REC_BYTES + 2 * YCH_BYTES + 128 + 64;       // scatter: 8128
@@ -238,7 +241,7 @@ __global__ void k_sw2_scale_pad_cm(int N0, int N1, int K0, int K1, int sn0, int 
 // MODG: the grid is left phase-modulated (the inverse FFT pass along dim 0 undoes it, fftbi.cu); the flush is then a
 // plain RED of the accumulators and the per-row factor is never loaded
 template <bool MODG>
-__global__ void __launch_bounds__(SWARPS * 32, 4)
+__global__ void __launch_bounds__(SWARPS * 32, SW2_CTAS)
 k_sw2_gridding(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const float* __restrict__ rec,
                const float2* __restrict__ mod, const float2* __restrict__ y, float2* __restrict__ grid) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -437,7 +440,7 @@ item_done:;
 // MODG: the grid arrives phase-modulated (written so by the forward FFT pass along dim 0, fftbi.cu): rows enter the
 // window as they are
 template <bool MODG>
-__global__ void __launch_bounds__(SWARPS * 32, 4)
+__global__ void __launch_bounds__(SWARPS * 32, SW2_CTAS)
 k_sw2_interp(Sw2Geom g, const WorkItem* __restrict__ work, int n_work, const float* __restrict__ rec,
              const float2* __restrict__ mod, const float2* __restrict__ grid, float2* __restrict__ y) {
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -234,7 +234,7 @@ def test_gridding_kernels_agree_3d(dev, geom):
         assert rel(A.y2k(y), ref_k) < TOL
         assert rel(A.adjoint(y), ref_x) < TOL
         assert rel(A.selfadjoint(x), O.adjoint(O.forward(x).astype(numpy.complex64))) < TOL
-    # column-sweep gather (interp variant 3): register ring on the phase-modulated grid, forward FFT passes emit it
+    # column-sweep gather everywhere (interp variant 3; "auto" already runs it on modulated grids): planes through a cp.async ring
     if Kd[0] >= 10:
         A.set_variant(3, 0)
         assert A._kspace_modulated()

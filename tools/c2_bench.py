@@ -1,6 +1,8 @@
 """Timing of configurations 2 and 4 (2D 256^2, 32 coils, golden-angle radial)."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import variant_env            # B200NUFFT_VARIANT: experiment builds (tools/build_variant.sh)
 import numpy, torch, ctypes
 import pynufft_b200
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))

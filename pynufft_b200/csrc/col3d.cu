@@ -145,9 +145,12 @@ __device__ __forceinline__ int next_item(int* counter, int lane) {
 // Pre-pass of the scatter, one kernel: ys[c][i] = conj(P''_i) * y[perm[i], c] (8-byte slots, coil stride Mpad), the grid
 // zero-fill (when the caller's grid is not known to be zero) and the reset of the persistent kernel's work counters.
 // The data gather is a chain of two dependent loads per sample (side entry -> y[perm]): a thread takes GU samples at
-// a time, all side loads first, then all y loads (four independent chains in flight per thread), and the zero-fill
+// a time, all side loads first, then all y loads (GU independent chains in flight per thread), and the zero-fill
 // stores of the thread are issued between the two so that the store stream covers part of the latency.
-constexpr int GU = 4;
+#ifndef COL_GU
+#define COL_GU 2       // measured 2 / 4 / 8: gridding stage 227.4 / 229.3 / 233.7 us
+#endif
+constexpr int GU = COL_GU;
 __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M, long long Mpad,
                                     const float2* __restrict__ y, float2* __restrict__ ys, int nb,
                                     float4* __restrict__ grid4, long long n4, int* __restrict__ counters) {

@@ -206,10 +206,13 @@ __global__ void k_gather_sorted_col(const float4* __restrict__ side, long long M
 #ifndef COL_S_CTAS
 #define COL_S_CTAS 4
 #endif
+// DEMOD = true: the retired plane is demodulated on its way out (conj(m0[plane] m1[row] m2[column]) per cell), so that the
+// REDs build the TRUE grid the y2k stage of the API returns -- no separate demodulation pass over the grid.
+template <bool DEMOD>
 __global__ void __launch_bounds__(CWARPS * 32, COL_S_CTAS)
 k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __restrict__ counter,
                const float* __restrict__ rec, const float2* __restrict__ ys, long long Mpad, float2* __restrict__ grid,
-               int coil0) {
+               int coil0, const float2* __restrict__ mod) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* ws = smem_raw + warp * GWARP_BYTES;
@@ -238,6 +241,7 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
         const int q1 = wi.tile / g.nq2, q2 = wi.tile - q1 * g.nq2;
         // this lane's three cells inside plane 0
         float2* cell[CNR];
+        float2 f12[CNR];               // DEMOD: conj(m1[row] m2[column]) of this lane's cells
         {
             int col = q2 * CT2 + lc;
             if (col >= g.K2) col -= g.K2;
@@ -246,6 +250,10 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
                 int row = q1 * CT1 + lg + 3 * i;
                 if (row >= g.K1) row -= g.K1;
                 cell[i] = gc + (row * g.K2 + col);
+                if (DEMOD) {
+                    const float2 t = cmul(__ldg(mod + g.K0 + row), __ldg(mod + g.K0 + g.K1 + col));
+                    f12[i] = make_float2(t.x, -t.y);
+                }
             }
         }
         const int nchunks = (wi.end - wi.begin + CCH - 1) / CCH;
@@ -332,9 +340,16 @@ k_gridding_col(ColGeom g, const WorkItem* __restrict__ work, int n_work, int* __
             nrun = pr.y;                                                                           \
         }                                                                                          \
         if (COL_S_RED) {                                                                           \
-            red_v2(cp0, A[KC][0]);                                                                 \
-            red_v2(cp1, A[KC][1]);                                                                 \
-            red_v2(cp2, A[KC][2]);                                                                 \
+            if (DEMOD) {                                                                           \
+                const float2 f0 = __ldg(mod + pw);                                                 \
+                red_v2(cp0, cmul(A[KC][0], cmulc(f0, f12[0])));                                    \
+                red_v2(cp1, cmul(A[KC][1], cmulc(f0, f12[1])));                                    \
+                red_v2(cp2, cmul(A[KC][2], cmulc(f0, f12[2])));                                    \
+            } else {                                                                               \
+                red_v2(cp0, A[KC][0]);                                                             \
+                red_v2(cp1, A[KC][1]);                                                             \
+                red_v2(cp2, A[KC][2]);                                                             \
+            }                                                                                      \
         }                                                                                          \
         _Pragma("unroll") for (int i = 0; i < CNR; ++i) A[KC][i] = make_float2(0.f, 0.f);          \
         cp0 += KK; cp1 += KK; cp2 += KK;                                                           \
@@ -725,7 +740,8 @@ static int col_ctas(b200nufft_plan_t p, int nb, int resident) {
 
 static int col_attrs(b200nufft_plan_t p) {
     if (!p->attr_col) {
-        CUDA_TRY(cudaFuncSetAttribute(k_gridding_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_gridding_col<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(k_gridding_col<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * GWARP_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(k_interp_col, cudaFuncAttributeMaxDynamicSharedMemorySize, CWARPS * IWARP_BYTES));
         p->attr_col = true;
     }
@@ -778,8 +794,9 @@ int col3d_interp(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cuda
     return B200_OK;
 }
 
-// grid receives the phase-modulated adjoint (it is zeroed here, by the pre-pass, unless the caller hands in a zeroed one)
-int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool prezeroed) {
+// grid receives the phase-modulated adjoint -- or, with `demodulate`, the true grid -- (it is zeroed here, by the pre-pass,
+// unless the caller hands in a zeroed one)
+int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool prezeroed, bool demodulate) {
     int rc = col_attrs(p);
     if (rc) return rc;
     const long long nel = p->g.Kprod * nb;
@@ -811,8 +828,12 @@ int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cu
     for (int c0 = 0; c0 < nb; c0 += COL_COILS) {     // coil groups: see col3d_interp
         const int nbg = std::min(COL_COILS, nb - c0);
         dim3 gr((unsigned)std::min((p->n_cwork + CWARPS - 1) / CWARPS, col_ctas(p, nbg, COL_S_CTAS)), nbg);
-        k_gridding_col<<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
-                                                                     p->d_crec, p->d_ys2, Mpad, grid, c0);
+        if (demodulate)
+            k_gridding_col<true><<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
+                                                                               p->d_crec, p->d_ys2, Mpad, grid, c0, p->d_mod);
+        else
+            k_gridding_col<false><<<gr, CWARPS * 32, CWARPS * GWARP_BYTES, st>>>(col_geom(p->g), p->d_cwork, p->n_cwork, p->d_ccount,
+                                                                                p->d_crec, p->d_ys2, Mpad, grid, c0, nullptr);
         LAUNCH_CHECK();
     }
     return B200_OK;

@@ -257,7 +257,8 @@ int ensure_scratch2(b200nufft_plan_t p, int nb);
 // col3d.cu: register-resident column-sweep gridding (3-D, J = 6); the grid it produces is phase-modulated
 bool col3d_supported(const Geom& g);
 // zeroes the grid itself (inside its pre-pass kernel)
-int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st, bool prezeroed = false);
+int col3d_gridding(b200nufft_plan_t p, const float2* y, float2* grid_mod, int nb, cudaStream_t st, bool prezeroed = false,
+                   bool demodulate = false);
 int col3d_demodulate(b200nufft_plan_t p, float2* grid, int nb, cudaStream_t st);
 // register-resident column-sweep gather on the phase-modulated grid (needs K0 >= 8)
 bool col3d_interp_supported(const Geom& g);

@@ -136,11 +136,8 @@ int interp_impl(b200nufft_plan_t p, const float2* grid, float2* y, int nb, cudaS
 // modulated_ok: the caller takes the grid phase-modulated when the column-sweep kernel ran (gridding_modulated(p));
 // otherwise the true grid is returned (one extra pass after the column-sweep kernel).
 int gridding_impl(b200nufft_plan_t p, const float2* y, float2* grid, int nb, cudaStream_t st, bool modulated_ok) {
-    if (p->M > 0 && gridding_modulated(p)) {         // zeroes the grid itself, inside its pre-pass kernel
-        int rc = col3d_gridding(p, y, grid, nb, st);
-        if (rc || modulated_ok) return rc;
-        return col3d_demodulate(p, grid, nb, st);
-    }
+    if (p->M > 0 && gridding_modulated(p))           // zeroes the grid itself, inside its pre-pass kernel; a caller that wants
+        return col3d_gridding(p, y, grid, nb, st, false, !modulated_ok);   // the true grid gets the demodulating instantiation
     if (p->M > 0 && use_bi(p, nb))               // batch-innermost grid, zero-fills; modulated when the caller takes it so
         return sweep2d_gridding(p, y, grid, nb, st, modulated_ok && bi_fused_mod(p, nb));
     CUDA_TRY(cudaMemsetAsync(grid, 0, sizeof(float2) * p->g.Kprod * nb, st));

@@ -483,10 +483,14 @@ static int adjoint_impl(b200nufft_plan_t p, const float2* y, float2* x, int nb, 
     }
     int rc = ensure_scratch(p, nb);
     if (rc) return rc;
-    rc = gridding_impl(p, y, p->d_grid, nb, as_stream(stream), true);
+    // 3-D column sweep in front of cuFFT (no fused passes at this size): ask the scatter for the true grid -- its
+    // demodulating instantiation -- instead of a demodulation pass over the grid in front of the inverse FFT
+    const bool col3 = p->M > 0 && gridding_modulated(p) && !use_bi(p, nb);
+    const bool keep_mod = !col3 || (p->fft_variant != 1 && fft256_supported(p->g));
+    rc = gridding_impl(p, y, p->d_grid, nb, as_stream(stream), keep_mod);
     if (rc) return rc;
     return ifft_crop_impl(p, reinterpret_cast<b200_c64*>(p->d_grid), reinterpret_cast<b200_c64*>(x), nb, 1,
-                          combine, reinterpret_cast<const b200_c64*>(sens), stream, true);
+                          combine, reinterpret_cast<const b200_c64*>(sens), stream, keep_mod);
 }
 
 extern "C" int b200nufft_forward(b200nufft_plan_t p, const b200_c64* x, b200_c64* y, int nb, void* stream) {
